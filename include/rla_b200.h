@@ -1,0 +1,147 @@
+/*
+ * rla_b200.h -- C ABI of librla_b200.so: the B200 (sm_100a) implementation of rulinalg's
+ * dense hot path.  Plain pointers and sizes only; no torch / C++ types cross this boundary.
+ *
+ * Every entry point names the reference interface (file:line relative to the rulinalg tree)
+ * that it replaces or serves.  INTEGRATION.md shows the Rust binding a maintainer adds.
+ *
+ * Conventions
+ *   - return value: RLA_OK (0), a positive numerical status (RLA_ERR_SINGULAR -> Rust
+ *     ErrorKind::DivByZero, src/error.rs:10-34), or a negative environment error (CUDA, no
+ *     device, out of memory).  Nothing throws or unwinds across the boundary.
+ *   - shape violations are asserted on the Rust side before the call (mat_mul.rs:21,
+ *     lu.rs:165,232); the C layer re-checks only what would make it read out of bounds.
+ *   - host pointers are borrowed for the duration of the call; nothing is retained.
+ *   - there is NO CPU fallback: without a usable sm_100 device every compute entry point
+ *     returns RLA_ERR_NO_DEVICE.
+ *   - all matrices are row-major; "ld*" / "rs*" are row strides in ELEMENTS.
+ */
+#ifndef RLA_B200_H
+#define RLA_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define RLA_API __attribute__((visibility("default")))
+#else
+#define RLA_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RLA_OK 0
+#define RLA_ERR_SINGULAR 1      /* |pivot| < epsilon  -> ErrorKind::DivByZero                */
+#define RLA_ERR_INVALID 2       /* bad argument (negative stride on an output, null pointer) */
+#define RLA_ERR_CUDA (-1)       /* a CUDA call failed; see rla_last_cuda_error()             */
+#define RLA_ERR_NOMEM (-2)      /* device or pinned-host allocation failed                   */
+#define RLA_ERR_NO_DEVICE (-3)  /* no sm_100 device visible (there is no CPU fallback)       */
+
+/* ---------------------------------------------------------------------------------------
+ * Host-pointer entry points: the drop-in boundary.
+ * ------------------------------------------------------------------------------------- */
+
+/* Replaces matrixmultiply::dgemm at src/matrix/mat_mul.rs:57-67 (same argument order and
+ * meaning): C <- alpha*A*B + beta*C, A is m x k, B is k x n, C is m x n, element (i,j) of X
+ * at x[i*rsx + j*csx].  rulinalg always passes csa=csb=csc=1, alpha=1, beta=0, and C
+ * uninitialised (mat_mul.rs:52-55): with beta == 0 C is never read and every element is
+ * written.  k == 0 with beta == 0 zero-fills C.  Unit column strides are the fast path;
+ * other strides are packed on the host first. */
+RLA_API int rla_dgemm(size_t m, size_t k, size_t n, double alpha,
+              const double *a, ptrdiff_t rsa, ptrdiff_t csa,
+              const double *b, ptrdiff_t rsb, ptrdiff_t csb,
+              double beta, double *c, ptrdiff_t rsc, ptrdiff_t csc);
+
+/* Replaces matrixmultiply::sgemm at src/matrix/mat_mul.rs:33-43.  FP32 FFMA arithmetic, no
+ * TF32 / tensor cores, so accuracy class matches the reference. */
+RLA_API int rla_sgemm(size_t m, size_t k, size_t n, float alpha,
+              const float *a, ptrdiff_t rsa, ptrdiff_t csa,
+              const float *b, ptrdiff_t rsb, ptrdiff_t csb,
+              float beta, float *c, ptrdiff_t rsc, ptrdiff_t csc);
+
+/* Replaces the body of PartialPivLu::decompose (src/matrix/decomposition/lu.rs:163-195 with
+ * gaussian_elimination :603-616).  `lu` is the n x n row-major contiguous matrix, factorised
+ * in place into packed L\U (unit diagonal of L implicit).  `perm` (length n) receives
+ * PartialPivLu.p.perm, i.e. the permutation AFTER p.inverse() (lu.rs:192):
+ * perm[original_row] = final_position, P*A = L*U.  Pivot rule: first row attaining
+ * max |a_ik| (lu.rs:173-178).  Returns RLA_ERR_SINGULAR when a pivot has |p| < DBL_EPSILON
+ * (lu.rs:179-183); `lu` content is then unspecified (the reference drops the matrix). */
+RLA_API int rla_dgetrf(size_t n, double *lu, size_t *perm);
+RLA_API int rla_sgetrf(size_t n, float *lu, size_t *perm);      /* T = f32: FLT_EPSILON */
+
+/* Replaces the body of PartialPivLu::solve (lu.rs:231-244): b <- U^-1 L^-1 P b with
+ * P b = permute_vector_into_buffer (permutation_matrix.rs:369-382), unit-lower forward
+ * substitution (lu.rs:624-642) and back_substitution (src/matrix/mod.rs:318-357), whose
+ * |u_ii| < epsilon test returns RLA_ERR_SINGULAR ("Lower triangular matrix is singular to
+ * working precision.", mod.rs:334-335).  On error b is left untouched. */
+RLA_API int rla_dgetrs(size_t n, const double *lu, const size_t *perm, double *b);
+RLA_API int rla_sgetrs(size_t n, const float *lu, const size_t *perm, float *b);
+
+/* Factorisation kept resident in HBM for repeated solves (PartialPivLu is built for "multiple
+ * such linear systems involving the same A", lu.rs:203-206).  rla_dgetrf_keep = rla_dgetrf
+ * that also returns a handle; rla_lu_solve = rla_dgetrs without re-uploading lu. */
+typedef struct rla_lu_handle rla_lu_handle;
+RLA_API int rla_dgetrf_keep(size_t n, double *lu, size_t *perm, rla_lu_handle **out);
+RLA_API int rla_dlu_solve(const rla_lu_handle *h, double *b);
+RLA_API void rla_lu_free(rla_lu_handle *h);
+
+/* ---------------------------------------------------------------------------------------
+ * Device-resident twins (kernel timing, multi-GPU sharding, LU -> solve reuse).
+ * All pointers are device pointers on the current device; `stream` is a cudaStream_t passed
+ * as void* (NULL = the library's own per-thread stream).  Calls are asynchronous on that
+ * stream unless stated.
+ * ------------------------------------------------------------------------------------- */
+RLA_API int rla_init(int device);                 /* select device + create context; idempotent      */
+RLA_API int rla_device_count(void);
+RLA_API int rla_dev_alloc(void **p, size_t bytes);
+RLA_API int rla_dev_free(void *p);
+RLA_API int rla_host_alloc_pinned(void **p, size_t bytes);
+RLA_API int rla_host_free_pinned(void *p);
+RLA_API int rla_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream);
+RLA_API int rla_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream);
+RLA_API int rla_stream_sync(void *stream);
+
+/* C <- alpha*A*B + beta*C on device, unit column strides (the mat_mul.rs fast path).
+ * f64: FP64 tensor-core (DMMA, mma.sync.m8n8k4.f64) kernel; f32: register-blocked FFMA. */
+RLA_API int rla_dgemm_dev(size_t m, size_t k, size_t n, double alpha,
+                  const double *a, size_t lda, const double *b, size_t ldb,
+                  double beta, double *c, size_t ldc, void *stream);
+RLA_API int rla_sgemm_dev(size_t m, size_t k, size_t n, float alpha,
+                  const float *a, size_t lda, const float *b, size_t ldb,
+                  float beta, float *c, size_t ldc, void *stream);
+
+/* Blocked right-looking LU with partial pivoting on an n x n matrix with row stride ld.
+ * d_perm: int64[n] device, same meaning as rla_dgetrf's perm.  d_info: int32 device scalar,
+ * 0 = ok, j+1 = |pivot| < epsilon at column j.  Workspace is owned by the library. */
+RLA_API int rla_dgetrf_dev(size_t n, double *a, size_t ld, int64_t *d_perm, int32_t *d_info, void *stream);
+RLA_API int rla_sgetrf_dev(size_t n, float *a, size_t ld, int64_t *d_perm, int32_t *d_info, void *stream);
+
+/* Solve with a device-resident factorisation: d_b (length n) is overwritten with x.
+ * d_info: 0 = ok, i+1 = |u_ii| < epsilon (then d_b is unspecified). */
+RLA_API int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm,
+                   double *d_b, int32_t *d_info, void *stream);
+RLA_API int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm,
+                   float *d_b, int32_t *d_info, void *stream);
+
+/* Seeded U[lo, lo+scale) fill, bit-identical to the test oracle's generator, so that every
+ * rank can synthesise its shard in HBM without a transfer.  Element (i,j) of the rows x cols
+ * matrix uses counter offset + (row0+i)*cols_total + (col0+j). */
+RLA_API int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
+                             uint64_t offset, double lo, double scale, void *stream);
+RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
+                             uint64_t offset, float lo, float scale, void *stream);
+
+/* Diagnostics */
+RLA_API const char *rla_strerror(int status);
+RLA_API int rla_last_cuda_error(void);            /* cudaError_t of the last failing CUDA call (per thread) */
+RLA_API const char *rla_version(void);
+/* number of kernels this library has launched in the calling thread since the last reset */
+RLA_API uint64_t rla_launch_count(void);
+RLA_API void rla_launch_count_reset(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RLA_B200_H */

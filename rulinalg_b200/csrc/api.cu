@@ -1,0 +1,482 @@
+// api.cu -- the extern "C" boundary of librla_b200.so (see include/rla_b200.h).
+//
+// Host-pointer entry points = stage operands into HBM, run the device twin, copy the result back.
+// There is no CPU compute path here: if no sm_100 device is usable every call returns
+// RLA_ERR_NO_DEVICE.  One context per host thread (stream + grow-only device/pinned buffers), so the
+// library is re-entrant like the single-threaded reference is (Matrix<T>: Send + Sync).
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "common.cuh"
+
+namespace rla {
+
+namespace {
+
+thread_local cudaError_t tl_last_cuda = cudaSuccess;
+thread_local uint64_t tl_launches = 0;
+
+struct Buffer {
+    void *p = nullptr;
+    size_t cap = 0;
+    bool pinned_host = false;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return RLA_OK;
+        release();
+        // grow geometrically to avoid realloc churn on size sweeps
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            want = bytes;
+            e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+        }
+        if (e != cudaSuccess) {
+            p = nullptr;
+            note_cuda_error(e);
+            cudaGetLastError();
+            return RLA_ERR_NOMEM;
+        }
+        cap = want;
+        return RLA_OK;
+    }
+    void release() {
+        if (p) {
+            if (pinned_host) cudaFreeHost(p); else cudaFree(p);
+        }
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct Context {
+    bool ready = false;
+    int device = -1;
+    cudaStream_t stream = nullptr;       // compute
+    cudaStream_t copy_in = nullptr;      // H2D
+    cudaStream_t copy_out = nullptr;     // D2H
+    Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync;
+    Buffer hStage[2];                    // pinned bounce buffers for pageable operands
+    Buffer hSmall;                       // pinned scalars (info, perm)
+    LuWorkspace lu_ws;
+    std::vector<cudaEvent_t> events;
+    Context() {
+        hStage[0].pinned_host = hStage[1].pinned_host = true;
+        hSmall.pinned_host = true;
+    }
+};
+thread_local Context tl_ctx;
+
+std::once_flag g_dev_once;
+int g_dev_status = RLA_ERR_NO_DEVICE;
+int g_dev_count = 0;
+
+void probe_devices() {
+    int cnt = 0;
+    cudaError_t e = cudaGetDeviceCount(&cnt);
+    if (e != cudaSuccess || cnt == 0) {
+        cudaGetLastError();
+        g_dev_status = RLA_ERR_NO_DEVICE;
+        return;
+    }
+    g_dev_count = cnt;
+    g_dev_status = RLA_OK;
+}
+
+int ensure_ctx(int device = -1) {
+    std::call_once(g_dev_once, probe_devices);
+    if (g_dev_status != RLA_OK) return g_dev_status;
+    Context &c = tl_ctx;
+    if (c.ready && (device < 0 || device == c.device)) return RLA_OK;
+    if (device < 0) {
+        if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return RLA_ERR_NO_DEVICE; }
+    }
+    if (device >= g_dev_count) return RLA_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    RLA_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return RLA_ERR_NO_DEVICE;   // kernels are sm_100a only; no fallback
+    RLA_CUDA(cudaSetDevice(device));
+    if (!c.stream) RLA_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (!c.copy_in) RLA_CUDA(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
+    if (!c.copy_out) RLA_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
+    c.device = device;
+    c.ready = true;
+    return RLA_OK;
+}
+
+cudaStream_t pick_stream(void *s) { return s ? static_cast<cudaStream_t>(s) : tl_ctx.stream; }
+
+bool is_pinned(const void *p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// Row-strided host matrix -> contiguous-ish device matrix (ld elements per row).
+template <typename T>
+int upload_matrix(T *dst, size_t ld, const T *src, size_t rs, size_t rows, size_t cols, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return RLA_OK;
+    RLA_CUDA(cudaMemcpy2DAsync(dst, ld * sizeof(T), src, rs * sizeof(T), cols * sizeof(T), rows, cudaMemcpyHostToDevice, st));
+    return RLA_OK;
+}
+template <typename T>
+int download_matrix(T *dst, size_t rs, const T *src, size_t ld, size_t rows, size_t cols, cudaStream_t st) {
+    if (rows == 0 || cols == 0) return RLA_OK;
+    RLA_CUDA(cudaMemcpy2DAsync(dst, rs * sizeof(T), src, ld * sizeof(T), cols * sizeof(T), rows, cudaMemcpyDeviceToHost, st));
+    return RLA_OK;
+}
+
+inline size_t pad_ld(size_t cols, size_t elem) {
+    const size_t q = 16 / elem;          // keep rows 16-byte aligned so the cp.async fast path applies
+    return (cols + q - 1) / q * q;
+}
+
+template <typename T>
+int gemm_dev(size_t m, size_t k, size_t n, T alpha, const T *a, size_t lda, const T *b, size_t ldb, T beta, T *c,
+             size_t ldc, cudaStream_t st);
+template <>
+int gemm_dev<double>(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b,
+                     size_t ldb, double beta, double *c, size_t ldc, cudaStream_t st) {
+    return dgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+}
+template <>
+int gemm_dev<float>(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b,
+                    size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
+    return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+}
+
+// Host operand with arbitrary (possibly negative / non-unit) strides -> packed row-major copy.
+template <typename T>
+void pack_host(std::vector<T> &out, const T *src, ptrdiff_t rs, ptrdiff_t cs, size_t rows, size_t cols) {
+    out.resize(rows * cols);
+    for (size_t i = 0; i < rows; ++i)
+        for (size_t j = 0; j < cols; ++j) out[i * cols + j] = src[ptrdiff_t(i) * rs + ptrdiff_t(j) * cs];
+}
+
+// The host-pointer GEMM.  Pipeline: B is uploaded whole (it is reused by every row panel); A is
+// uploaded and C downloaded in row panels so PCIe transfers overlap the kernel of the previous /
+// next panel (three streams, events).
+template <typename T>
+int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, ptrdiff_t csa, const T *b,
+              ptrdiff_t rsb, ptrdiff_t csb, T beta, T *c, ptrdiff_t rsc, ptrdiff_t csc) {
+    if (m == 0 || n == 0) return RLA_OK;
+    if ((k > 0 && (!a || !b)) || !c) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+
+    std::vector<T> pa, pb, pc;
+    const T *ha = a, *hb = b;
+    size_t hrsa = size_t(rsa), hrsb = size_t(rsb);
+    if (k > 0 && (csa != 1 || rsa < ptrdiff_t(k))) { pack_host(pa, a, rsa, csa, m, k); ha = pa.data(); hrsa = k; }
+    if (k > 0 && (csb != 1 || rsb < ptrdiff_t(n))) { pack_host(pb, b, rsb, csb, k, n); hb = pb.data(); hrsb = n; }
+    const bool c_direct = (csc == 1 && rsc >= ptrdiff_t(n));
+    T *hc = c;
+    size_t hrsc = size_t(rsc);
+    if (!c_direct) {
+        if (beta != T(0)) pack_host(pc, c, rsc, csc, m, n); else pc.resize(m * n);
+        hc = pc.data();
+        hrsc = n;
+    }
+
+    const size_t lda = pad_ld(k ? k : 1, sizeof(T)), ldb = pad_ld(n, sizeof(T)), ldc = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(m * lda * sizeof(T)));
+    RLA_TRY(cx.dB.ensure((k ? k : 1) * ldb * sizeof(T)));
+    RLA_TRY(cx.dC.ensure(m * ldc * sizeof(T)));
+    T *dA = static_cast<T *>(cx.dA.p), *dB = static_cast<T *>(cx.dB.p), *dC = static_cast<T *>(cx.dC.p);
+
+    // row-panel pipeline: panel height chosen so that a panel is >= ~32 MiB of A+C traffic
+    size_t panel = m;
+    const size_t bytes_per_row = (k + n) * sizeof(T);
+    if (m * bytes_per_row > (size_t(96) << 20)) {
+        panel = ((size_t(32) << 20) / bytes_per_row + 127) / 128 * 128;
+        if (panel < 128) panel = 128;
+        if (panel > m) panel = m;
+    }
+    const size_t npanels = (m + panel - 1) / panel;
+    while (cx.events.size() < 2 * npanels + 1) {
+        cudaEvent_t e;
+        RLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        cx.events.push_back(e);
+    }
+    RLA_TRY(upload_matrix(dB, ldb, hb, hrsb, k, n, cx.copy_in));
+    for (size_t p = 0; p < npanels; ++p) {
+        const size_t r0 = p * panel, rows = (r0 + panel <= m) ? panel : m - r0;
+        RLA_TRY(upload_matrix(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, cx.copy_in));
+        if (beta != T(0)) RLA_TRY(upload_matrix(dC + r0 * ldc, ldc, hc + r0 * hrsc, hrsc, rows, n, cx.copy_in));
+        RLA_CUDA(cudaEventRecord(cx.events[2 * p], cx.copy_in));
+        RLA_CUDA(cudaStreamWaitEvent(cx.stream, cx.events[2 * p], 0));
+        RLA_TRY(gemm_dev<T>(rows, k, n, alpha, dA + r0 * lda, lda, dB, ldb, beta, dC + r0 * ldc, ldc, cx.stream));
+        RLA_CUDA(cudaEventRecord(cx.events[2 * p + 1], cx.stream));
+        RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * p + 1], 0));
+        RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, n, cx.copy_out));
+    }
+    RLA_CUDA(cudaStreamSynchronize(cx.copy_out));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (!c_direct)
+        for (size_t i = 0; i < m; ++i)
+            for (size_t j = 0; j < n; ++j) c[ptrdiff_t(i) * rsc + ptrdiff_t(j) * csc] = pc[i * n + j];
+    return RLA_OK;
+}
+
+template <typename T>
+int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm, size_t *keep_ld) {
+    if (n == 0) return RLA_OK;
+    if (!lu || !perm) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    T *dA;
+    int64_t *dP;
+    if (keep_dev) {
+        void *p1 = nullptr, *p2 = nullptr;
+        RLA_CUDA(cudaMalloc(&p1, n * ld * sizeof(T)));
+        cudaError_t e = cudaMalloc(&p2, n * sizeof(int64_t));
+        if (e != cudaSuccess) { cudaFree(p1); note_cuda_error(e); return RLA_ERR_NOMEM; }
+        dA = static_cast<T *>(p1);
+        dP = static_cast<int64_t *>(p2);
+    } else {
+        RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+        RLA_TRY(cx.dPerm.ensure(n * sizeof(int64_t)));
+        dA = static_cast<T *>(cx.dA.p);
+        dP = static_cast<int64_t *>(cx.dPerm.p);
+    }
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p);
+    int32_t *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    int st = upload_matrix(dA, ld, lu, n, n, n, cx.stream);
+    if (st == RLA_OK) st = getrf_launch<T>(n, dA, ld, dP, dInfo, cx.lu_ws, cx.stream);
+    if (st == RLA_OK) {
+        cudaError_t e = cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(cx.stream);
+        if (e != cudaSuccess) { note_cuda_error(e); st = RLA_ERR_CUDA; }
+    }
+    if (st == RLA_OK && *hInfo != 0) st = RLA_ERR_SINGULAR;
+    if (st == RLA_OK) {
+        st = download_matrix(lu, n, dA, ld, n, n, cx.stream);
+        static_assert(sizeof(size_t) == sizeof(int64_t), "LP64 expected");
+        if (st == RLA_OK) {
+            cudaError_t e = cudaMemcpyAsync(perm, dP, n * sizeof(int64_t), cudaMemcpyDeviceToHost, cx.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(cx.stream);
+            if (e != cudaSuccess) { note_cuda_error(e); st = RLA_ERR_CUDA; }
+        }
+    }
+    if (keep_dev) {
+        if (st == RLA_OK) {
+            *keep_dev = dA;
+            *keep_perm = dP;
+            *keep_ld = ld;
+        } else {
+            cudaFree(dA);
+            cudaFree(dP);
+        }
+    }
+    return st;
+}
+
+template <typename T>
+int getrs_core(size_t n, const T *dLU, size_t ld, const int64_t *dP, T *b) {
+    Context &cx = tl_ctx;
+    RLA_TRY(cx.dVec.ensure(n * sizeof(T)));
+    RLA_TRY(cx.dVec2.ensure(n * sizeof(T)));
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.dSync.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    T *dB = static_cast<T *>(cx.dVec.p), *dTmp = static_cast<T *>(cx.dVec2.p);
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p);
+    int32_t *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    RLA_CUDA(cudaMemcpyAsync(dB, b, n * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(getrs_launch<T>(n, dLU, ld, dP, dB, dTmp, dInfo, static_cast<int32_t *>(cx.dSync.p), cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*hInfo != 0) return RLA_ERR_SINGULAR;
+    RLA_CUDA(cudaMemcpyAsync(b, dB, n * sizeof(T), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
+template <typename T>
+int getrs_host(size_t n, const T *lu, const size_t *perm, T *b) {
+    if (n == 0) return RLA_OK;
+    if (!lu || !perm || !b) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dPerm.ensure(n * sizeof(int64_t)));
+    T *dA = static_cast<T *>(cx.dA.p);
+    int64_t *dP = static_cast<int64_t *>(cx.dPerm.p);
+    RLA_TRY(upload_matrix(dA, ld, lu, n, n, n, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(dP, perm, n * sizeof(int64_t), cudaMemcpyHostToDevice, cx.stream));
+    return getrs_core<T>(n, dA, ld, dP, b);
+}
+
+}  // namespace
+
+void note_cuda_error(cudaError_t e) { tl_last_cuda = e; }
+void note_launch(unsigned n) { tl_launches += n; }
+
+}  // namespace rla
+
+struct rla_lu_handle {
+    size_t n, ld;
+    double *lu;
+    int64_t *perm;
+    int device;
+};
+
+using namespace rla;
+
+extern "C" {
+
+int rla_dgemm(size_t m, size_t k, size_t n, double alpha, const double *a, ptrdiff_t rsa, ptrdiff_t csa,
+              const double *b, ptrdiff_t rsb, ptrdiff_t csb, double beta, double *c, ptrdiff_t rsc, ptrdiff_t csc) {
+    return gemm_host<double>(m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, rsc, csc);
+}
+int rla_sgemm(size_t m, size_t k, size_t n, float alpha, const float *a, ptrdiff_t rsa, ptrdiff_t csa, const float *b,
+              ptrdiff_t rsb, ptrdiff_t csb, float beta, float *c, ptrdiff_t rsc, ptrdiff_t csc) {
+    return gemm_host<float>(m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, rsc, csc);
+}
+int rla_dgetrf(size_t n, double *lu, size_t *perm) { return getrf_host<double>(n, lu, perm, nullptr, nullptr, nullptr); }
+int rla_sgetrf(size_t n, float *lu, size_t *perm) { return getrf_host<float>(n, lu, perm, nullptr, nullptr, nullptr); }
+int rla_dgetrs(size_t n, const double *lu, const size_t *perm, double *b) { return getrs_host<double>(n, lu, perm, b); }
+int rla_sgetrs(size_t n, const float *lu, const size_t *perm, float *b) { return getrs_host<float>(n, lu, perm, b); }
+
+int rla_dgetrf_keep(size_t n, double *lu, size_t *perm, rla_lu_handle **out) {
+    if (!out) return RLA_ERR_INVALID;
+    *out = nullptr;
+    double *dA = nullptr;
+    int64_t *dP = nullptr;
+    size_t ld = 0;
+    if (n == 0) {
+        rla_lu_handle *h = new rla_lu_handle{0, 0, nullptr, nullptr, 0};
+        *out = h;
+        return RLA_OK;
+    }
+    int st = getrf_host<double>(n, lu, perm, &dA, &dP, &ld);
+    if (st != RLA_OK) return st;
+    *out = new rla_lu_handle{n, ld, dA, dP, tl_ctx.device};
+    return RLA_OK;
+}
+int rla_dlu_solve(const rla_lu_handle *h, double *b) {
+    if (!h) return RLA_ERR_INVALID;
+    if (h->n == 0) return RLA_OK;
+    if (!b) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    return getrs_core<double>(h->n, h->lu, h->ld, h->perm, b);
+}
+void rla_lu_free(rla_lu_handle *h) {
+    if (!h) return;
+    if (h->lu) cudaFree(h->lu);
+    if (h->perm) cudaFree(h->perm);
+    delete h;
+}
+
+int rla_init(int device) { return ensure_ctx(device); }
+int rla_device_count(void) {
+    std::call_once(g_dev_once, probe_devices);
+    return g_dev_count;
+}
+int rla_dev_alloc(void **p, size_t bytes) {
+    if (!p) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    RLA_CUDA(cudaMalloc(p, bytes ? bytes : 1));
+    return RLA_OK;
+}
+int rla_dev_free(void *p) {
+    if (p) RLA_CUDA(cudaFree(p));
+    return RLA_OK;
+}
+int rla_host_alloc_pinned(void **p, size_t bytes) {
+    if (!p) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    RLA_CUDA(cudaMallocHost(p, bytes ? bytes : 1));
+    return RLA_OK;
+}
+int rla_host_free_pinned(void *p) {
+    if (p) RLA_CUDA(cudaFreeHost(p));
+    return RLA_OK;
+}
+int rla_memcpy_h2d(void *dst, const void *src, size_t bytes, void *stream) {
+    RLA_TRY(ensure_ctx());
+    RLA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, pick_stream(stream)));
+    return RLA_OK;
+}
+int rla_memcpy_d2h(void *dst, const void *src, size_t bytes, void *stream) {
+    RLA_TRY(ensure_ctx());
+    RLA_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, pick_stream(stream)));
+    return RLA_OK;
+}
+int rla_stream_sync(void *stream) {
+    RLA_TRY(ensure_ctx());
+    RLA_CUDA(cudaStreamSynchronize(pick_stream(stream)));
+    return RLA_OK;
+}
+
+int rla_dgemm_dev(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
+                  double beta, double *c, size_t ldc, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return dgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, pick_stream(stream));
+}
+int rla_sgemm_dev(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b, size_t ldb,
+                  float beta, float *c, size_t ldc, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, pick_stream(stream));
+}
+int rla_dgetrf_dev(size_t n, double *a, size_t ld, int64_t *d_perm, int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return getrf_launch<double>(n, a, ld, d_perm, d_info, tl_ctx.lu_ws, pick_stream(stream));
+}
+int rla_sgetrf_dev(size_t n, float *a, size_t ld, int64_t *d_perm, int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return getrf_launch<float>(n, a, ld, d_perm, d_info, tl_ctx.lu_ws, pick_stream(stream));
+}
+int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm, double *d_b, int32_t *d_info,
+                   void *stream) {
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    RLA_TRY(cx.dVec2.ensure(n * sizeof(double)));
+    RLA_TRY(cx.dSync.ensure(64));
+    return getrs_launch<double>(n, lu, ld, d_perm, d_b, static_cast<double *>(cx.dVec2.p), d_info,
+                                static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
+}
+int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, float *d_b, int32_t *d_info,
+                   void *stream) {
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    RLA_TRY(cx.dVec2.ensure(n * sizeof(float)));
+    RLA_TRY(cx.dSync.ensure(64));
+    return getrs_launch<float>(n, lu, ld, d_perm, d_b, static_cast<float *>(cx.dVec2.p), d_info,
+                               static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
+}
+int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
+                             double lo, double scale, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return fill_uniform_launch<double>(dst, rows, cols, ld, seed, offset, lo, scale, pick_stream(stream));
+}
+int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset, float lo,
+                             float scale, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return fill_uniform_launch<float>(dst, rows, cols, ld, seed, offset, lo, scale, pick_stream(stream));
+}
+
+const char *rla_strerror(int status) {
+    switch (status) {
+        case RLA_OK: return "ok";
+        case RLA_ERR_SINGULAR: return "matrix is singular to working precision (ErrorKind::DivByZero)";
+        case RLA_ERR_INVALID: return "invalid argument";
+        case RLA_ERR_CUDA: return "CUDA call failed (see rla_last_cuda_error)";
+        case RLA_ERR_NOMEM: return "device or pinned-host allocation failed";
+        case RLA_ERR_NO_DEVICE: return "no sm_100 (B200) device available; librla_b200 has no CPU fallback";
+        default: return "unknown status";
+    }
+}
+int rla_last_cuda_error(void) { return int(tl_last_cuda); }
+const char *rla_version(void) { return "rla_b200 0.1.0 (sm_100a)"; }
+uint64_t rla_launch_count(void) { return tl_launches; }
+void rla_launch_count_reset(void) { tl_launches = 0; }
+
+}  // extern "C"

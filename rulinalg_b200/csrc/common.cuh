@@ -1,0 +1,100 @@
+// common.cuh -- shared declarations for librla_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "../../include/rla_b200.h"
+
+namespace rla {
+
+// ---- per-thread error / launch accounting (api.cu) ---------------------------------------
+void note_cuda_error(cudaError_t e);
+void note_launch(unsigned n = 1);
+
+#define RLA_CUDA(expr)                                  \
+    do {                                                \
+        cudaError_t _e = (expr);                        \
+        if (_e != cudaSuccess) {                        \
+            ::rla::note_cuda_error(_e);                 \
+            return (_e == cudaErrorMemoryAllocation) ? RLA_ERR_NOMEM : RLA_ERR_CUDA; \
+        }                                               \
+    } while (0)
+
+#define RLA_TRY(expr)                 \
+    do {                              \
+        int _s = (expr);              \
+        if (_s != RLA_OK) return _s;  \
+    } while (0)
+
+// Checks the launch just issued and counts it.
+#define RLA_LAUNCHED()                                  \
+    do {                                                \
+        cudaError_t _e = cudaGetLastError();            \
+        if (_e != cudaSuccess) {                        \
+            ::rla::note_cuda_error(_e);                 \
+            return RLA_ERR_CUDA;                        \
+        }                                               \
+        ::rla::note_launch();                           \
+    } while (0)
+
+// ---- kernel launchers (one per .cu) ---------------------------------------------------------
+int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda,
+                 const double *b, size_t ldb, double beta, double *c, size_t ldc,
+                 cudaStream_t st);
+int sgemm_launch(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda,
+                 const float *b, size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st);
+
+// LU workspace: owned by the per-thread context, grown on demand.
+struct LuWorkspace {
+    int32_t *ipiv = nullptr;      // [n] pivot row chosen at each column (LAPACK-style, 0-based)
+    void *scratch = nullptr;      // panel scratch (candidates, barrier words, row buffers)
+    size_t ipiv_cap = 0, scratch_cap = 0;
+};
+template <typename T>
+int getrf_launch(size_t n, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws,
+                 cudaStream_t st);
+template <typename T>
+int getrs_launch(size_t n, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *d_tmp,
+                 int32_t *d_info, int32_t *d_flags, cudaStream_t st);
+
+template <typename T>
+int fill_uniform_launch(T *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
+                        uint64_t offset, T lo, T scale, cudaStream_t st);
+
+// ---- device helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+// 16-byte async copy global->shared; bytes beyond src_bytes are zero-filled (src_bytes in {0,8,16}).
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async8(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;\n" ::"r"(dst), "l"(src), "r"(src_bytes));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(N));
+}
+
+// FP64 tensor-core MMA: D(8x8) += A(8x4, row) * B(4x8, col).  SASS: DMMA.8x8x4.
+// Fragment ownership (lane = 4*g + t): A[g][t], B[t][g], C[g][2t], C[g][2t+1].
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+__host__ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+}  // namespace rla

@@ -1,0 +1,498 @@
+// lu.cu -- K3/K4/K5 + driver: blocked right-looking LU with partial (row) pivoting, row-major.
+//
+// Replaces the body of PartialPivLu::decompose (src/matrix/decomposition/lu.rs:163-195 with
+// gaussian_elimination :603-616).  Reference semantics kept exactly:
+//   * pivot = FIRST row attaining max |a_ik|, i >= k (strict '>' scan, lu.rs:173-178); a NaN never
+//     wins a comparison, a NaN on the diagonal stays the pivot;
+//   * |pivot| < epsilon (absolute) -> DivByZero (lu.rs:179-183) -> *info = k+1;
+//   * whole rows are swapped (lu.rs:185) -- including the already computed L part;
+//   * elimination arithmetic inside a panel is  m = a_ik / a_kk ; a_ij = a_ij - m*a_kj  with a
+//     separate multiply and subtract (no FMA contraction), each element receiving
+//     its updates in ascending k, so for n <= PW (one panel) the factors are bit-identical to the
+//     reference.  Beyond one panel the trailing updates run on the GEMM kernels (FMA/DMMA), which
+//     round differently (tolerance stated in DESIGN.md / tests).
+//
+// Structure (two-level): outer block W=256 columns, inner panels PW=64 columns.
+//   panel  : lu_panel_kernel   -- cooperative launch, <=1 CTA per SM, each CTA keeps its rows of the
+//                                 panel in shared memory; per column ONE grid-wide barrier: CTAs post
+//                                 (|max|, row, row contents), everyone reduces the posted candidates.
+//   laswp  : laswp_kernel      -- applies a block of row interchanges as ONE gather (net permutation
+//                                 computed by a warp with ballot search) instead of jb dependent swaps;
+//                                 also carries the row-origin vector from which `perm` is produced.
+//   trsm   : trsm_unit_lower_kernel -- U12 = L11^-1 A12, thread per column, column in registers.
+//   gemm   : dgemm_launch / sgemm_launch (alpha=-1, beta=1) for the Schur complement.
+#include <cfloat>
+#include <climits>
+#include <math_constants.h>
+
+#include "common.cuh"
+
+namespace rla {
+namespace {
+
+constexpr int PW = 64;          // inner panel width
+constexpr int OUTER_W = 256;    // outer block width
+constexpr int PANEL_THREADS = 512;
+constexpr int PLDS = PW + 1;    // padded smem row (odd => column sweeps are conflict-free)
+
+template <typename T> struct Eps;
+template <> struct Eps<double> { static __device__ __forceinline__ double v() { return DBL_EPSILON; } };
+template <> struct Eps<float> { static __device__ __forceinline__ float v() { return FLT_EPSILON; } };
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ double inf_of(double) { return CUDART_INF; }
+__device__ __forceinline__ float inf_of(float) { return CUDART_INF_F; }
+
+// better(a,ia | b,ib): candidate a beats b under the reference's scan order
+template <typename T>
+__device__ __forceinline__ bool cand_better(T va, int ia, T vb, int ib) {
+    return (va > vb) || (va == vb && ia < ib);
+}
+
+// -------------------------------------------------------------------------------------------
+// Panel factorisation of A[J:n, J:J+jb].  Grid = G CTAs (cooperative), CTA b owns rows
+// [J + b*R, J + (b+1)*R).  scratch: cand_abs[2][G], cand_idx[2][G], rowbuf[2][G][PW], diagbuf[2][PW].
+// -------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(PANEL_THREADS, 1)
+lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32_t *__restrict__ ipiv,
+                int32_t *__restrict__ info, T *cand_abs, int *cand_idx, T *rowbuf, T *diagbuf,
+                unsigned *bar, unsigned bar_base) {
+    if (*info != 0) return;   // an earlier panel hit a tiny pivot: written by a previous kernel => uniform
+    extern __shared__ __align__(16) unsigned char panel_smem[];
+    T *s = reinterpret_cast<T *>(panel_smem);
+    __shared__ T prow_s[PW];
+    __shared__ T red_abs[PANEL_THREADS / 32];
+    __shared__ int red_idx[PANEL_THREADS / 32];
+    __shared__ T sh_abs;
+    __shared__ int sh_idx, sh_win;
+
+    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int r0 = J + b * R;
+    const int r1 = min(n, r0 + R);
+    const int nrows = max(0, r1 - r0);
+
+    for (int idx = tid; idx < nrows * jb; idx += PANEL_THREADS) {
+        const int r = idx / jb, c = idx - r * jb;
+        s[r * PLDS + c] = A[size_t(r0 + r) * ld + J + c];
+    }
+    __syncthreads();
+
+    for (int c = 0; c < jb; ++c) {
+        const int d = J + c;                       // global diagonal row of this column
+        const int par = c & 1;
+        const int lo = max(0, d - r0);             // first local row still active
+        const bool owns_d = (d >= r0 && d < r1);
+
+        // ---- local argmax over active rows of column c (first max wins) ----
+        T best = T(-1);
+        int bidx = INT_MAX;
+        for (int r = lo + tid; r < nrows; r += PANEL_THREADS) {
+            const T v = fabs(s[r * PLDS + c]);
+            if (v > best) { best = v; bidx = r0 + r; }     // NaN: comparison false, never wins
+        }
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            const T ov = __shfl_down_sync(0xffffffffu, best, off);
+            const int oi = __shfl_down_sync(0xffffffffu, bidx, off);
+            if (cand_better(ov, oi, best, bidx)) { best = ov; bidx = oi; }
+        }
+        if (lane == 0) { red_abs[warp] = best; red_idx[warp] = bidx; }
+        __syncthreads();
+        if (warp == 0) {
+            best = (lane < PANEL_THREADS / 32) ? red_abs[lane] : T(-1);
+            bidx = (lane < PANEL_THREADS / 32) ? red_idx[lane] : INT_MAX;
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                const T ov = __shfl_down_sync(0xffffffffu, best, off);
+                const int oi = __shfl_down_sync(0xffffffffu, bidx, off);
+                if (cand_better(ov, oi, best, bidx)) { best = ov; bidx = oi; }
+            }
+            if (lane == 0) {
+                // reference starts the scan with curr_max = a_dd even when it is NaN (lu.rs:170-171):
+                // then no later row can win.  Post +inf for that row so it wins the global reduce.
+                if (owns_d) {
+                    const T dv = s[(d - r0) * PLDS + c];
+                    if (dv != dv) { best = inf_of(T(0)); bidx = d; }
+                }
+                sh_abs = best;
+                sh_idx = bidx;
+                cand_abs[par * G + b] = best;
+                cand_idx[par * G + b] = bidx;
+            }
+        }
+        __syncthreads();
+        // ---- post the candidate row (and the diagonal row) so the winner's contents are global ----
+        {
+            const int li = sh_idx;
+            if (li != INT_MAX && tid < jb) rowbuf[size_t(par * G + b) * PW + tid] = s[(li - r0) * PLDS + tid];
+            if (owns_d && tid >= 64 && tid < 64 + jb) diagbuf[par * PW + (tid - 64)] = s[(d - r0) * PLDS + (tid - 64)];
+        }
+        __threadfence();
+        __syncthreads();
+        // ---- grid-wide barrier (monotonic counter) ----
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(bar, 1u);
+            const unsigned target = bar_base + unsigned(c + 1) * unsigned(G);
+            while (int(*((volatile unsigned *)bar) - target) < 0) {
+            }
+            __threadfence();
+        }
+        __syncthreads();
+        // ---- global reduce over the G posted candidates (every CTA, redundantly) ----
+        if (warp == 0) {
+            T gv = T(-1);
+            int gi = INT_MAX, gw = 0;
+            for (int q = lane; q < G; q += 32) {
+                const T v = __ldcg(cand_abs + par * G + q);
+                const int i = __ldcg(cand_idx + par * G + q);
+                if (cand_better(v, i, gv, gi)) { gv = v; gi = i; gw = q; }
+            }
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) {
+                const T ov = __shfl_down_sync(0xffffffffu, gv, off);
+                const int oi = __shfl_down_sync(0xffffffffu, gi, off);
+                const int ow = __shfl_down_sync(0xffffffffu, gw, off);
+                if (cand_better(ov, oi, gv, gi)) { gv = ov; gi = oi; gw = ow; }
+            }
+            if (lane == 0) { sh_abs = gv; sh_idx = gi; sh_win = gw; }
+        }
+        __syncthreads();
+        const T pabs = sh_abs;
+        const int prow_idx = sh_idx, win = sh_win;
+        if (pabs < Eps<T>::v()) {                  // lu.rs:179-183 (NaN: comparison false, continues)
+            if (b == 0 && tid == 0) *info = d + 1;
+            return;                                // uniform across the grid
+        }
+        if (tid < jb) prow_s[tid] = __ldcg(rowbuf + size_t(par * G + win) * PW + tid);
+        if (b == 0 && tid == 0) ipiv[d] = prow_idx;
+        __syncthreads();
+        if (prow_idx != d) {                       // swap rows d <-> prow_idx inside the panel
+            if (owns_d && tid < jb) s[(d - r0) * PLDS + tid] = prow_s[tid];
+            if (prow_idx >= r0 && prow_idx < r1 && tid >= 64 && tid < 64 + jb)
+                s[(prow_idx - r0) * PLDS + (tid - 64)] = __ldcg(diagbuf + par * PW + (tid - 64));
+            __syncthreads();
+        }
+        // ---- multipliers (one IEEE division per row), then rank-1 update with mul, sub ----
+        const T piv = prow_s[c];
+        const int lo2 = max(0, d + 1 - r0);
+        for (int r = lo2 + tid; r < nrows; r += PANEL_THREADS) s[r * PLDS + c] = div_rn(s[r * PLDS + c], piv);
+        __syncthreads();
+        if (c + 1 < jb) {
+            for (int r = lo2 + warp; r < nrows; r += PANEL_THREADS / 32) {
+                const T m = s[r * PLDS + c];
+                for (int cc = c + 1 + lane; cc < jb; cc += 32)
+                    s[r * PLDS + cc] = sub_rn(s[r * PLDS + cc], mul_rn(m, prow_s[cc]));
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < nrows * jb; idx += PANEL_THREADS) {
+        const int r = idx / jb, c = idx - r * jb;
+        A[size_t(r0 + r) * ld + J + c] = s[r * PLDS + c];
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// laswp: apply interchanges (J+k <-> ipiv[J+k]), k = 0..jb-1, to columns [c0a,c1a) U [c0b,c1b) as one
+// gather.  "Touched" rows: index i < jb -> row J+i; index jb+f -> far row fr[f].  origin[i] = touched
+// index whose OLD contents end up in touched row i.  If rowid != nullptr CTA 0 also permutes it.
+// -------------------------------------------------------------------------------------------
+constexpr int LASWP_THREADS = 256;
+constexpr int LASWP_MAXJB = OUTER_W;
+
+template <typename T>
+__global__ void __launch_bounds__(LASWP_THREADS)
+laswp_kernel(T *__restrict__ A, size_t ld, int J, int jb, const int32_t *__restrict__ ipiv,
+             const int32_t *__restrict__ info, int c0a, int c1a, int c0b, int c1b, int CW,
+             int32_t *__restrict__ rowid) {
+    if (*info != 0) return;
+    extern __shared__ __align__(16) unsigned char laswp_smem[];
+    T *tile = reinterpret_cast<T *>(laswp_smem);
+    __shared__ int od[LASWP_MAXJB];       // origin of dense touched rows
+    __shared__ int fr[LASWP_MAXJB];       // far row numbers
+    __shared__ int of[LASWP_MAXJB];       // origin of far touched rows
+    __shared__ int piv_s[LASWP_MAXJB];
+    __shared__ int nf_s;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < jb; i += LASWP_THREADS) {
+        od[i] = i;
+        piv_s[i] = ipiv[J + i];
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int nf = 0;
+        for (int k = 0; k < jb; ++k) {
+            const int bq = piv_s[k];
+            if (bq == J + k) continue;
+            if (bq < J + jb) {
+                if (lane == 0) { const int t = od[k]; od[k] = od[bq - J]; od[bq - J] = t; }
+            } else {
+                int f = -1;
+                for (int base = 0; base < nf; base += 32) {
+                    const int q = base + lane;
+                    const unsigned hit = __ballot_sync(0xffffffffu, q < nf && fr[q] == bq);
+                    if (hit) { f = base + __ffs(hit) - 1; break; }
+                }
+                if (f < 0) {
+                    f = nf++;
+                    if (lane == 0) { fr[f] = bq; of[f] = jb + f; }
+                }
+                __syncwarp();
+                if (lane == 0) { const int t = od[k]; od[k] = of[f]; of[f] = t; }
+            }
+            __syncwarp();
+        }
+        if (lane == 0) nf_s = nf;
+    }
+    __syncthreads();
+    const int nf = nf_s;
+    const int nt = jb + nf;
+
+    // the row-origin vector rides along as one extra "column"
+    if (rowid != nullptr && blockIdx.x == 0) {
+        int *itile = reinterpret_cast<int *>(tile);
+        for (int i = tid; i < nt; i += LASWP_THREADS) itile[i] = rowid[(i < jb) ? J + i : fr[i - jb]];
+        __syncthreads();
+        for (int i = tid; i < nt; i += LASWP_THREADS) {
+            const int o = (i < jb) ? od[i] : of[i - jb];
+            if (o != i) rowid[(i < jb) ? J + i : fr[i - jb]] = itile[o];
+        }
+        __syncthreads();
+    }
+
+    const int na = c1a - c0a, ncols = na + (c1b - c0b);
+    const int chunk0 = blockIdx.x * CW;
+    if (chunk0 >= ncols) return;
+    const int cw = min(CW, ncols - chunk0);
+    // gather all touched rows of this column chunk
+    for (int i = warp; i < nt; i += LASWP_THREADS / 32) {
+        const int row = (i < jb) ? J + i : fr[i - jb];
+        const T *src = A + size_t(row) * ld;
+        for (int cc = lane; cc < cw; cc += 32) {
+            const int q = chunk0 + cc;
+            const int col = (q < na) ? c0a + q : c0b + (q - na);
+            tile[i * CW + cc] = src[col];
+        }
+    }
+    __syncthreads();
+    for (int i = warp; i < nt; i += LASWP_THREADS / 32) {
+        const int o = (i < jb) ? od[i] : of[i - jb];
+        if (o == i) continue;
+        const int row = (i < jb) ? J + i : fr[i - jb];
+        T *dst = A + size_t(row) * ld;
+        for (int cc = lane; cc < cw; cc += 32) {
+            const int q = chunk0 + cc;
+            const int col = (q < na) ? c0a + q : c0b + (q - na);
+            dst[col] = tile[o * CW + cc];
+        }
+    }
+}
+
+// -------------------------------------------------------------------------------------------
+// trsm: B <- L^-1 B, L = unit lower jb x jb (jb <= 64) at A[j:j+jb, j:j+jb], B = A[j:j+jb, c0:c1).
+// Thread per column, the column lives in registers; L is broadcast from shared memory.
+// -------------------------------------------------------------------------------------------
+constexpr int TRSM_THREADS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(TRSM_THREADS)
+trsm_unit_lower_kernel(T *__restrict__ A, size_t ld, int j, int jb, int c0, int c1,
+                       const int32_t *__restrict__ info) {
+    if (*info != 0) return;
+    __shared__ T Ls[PW * PW];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < PW * PW; idx += TRSM_THREADS) {
+        const int r = idx / PW, c = idx - r * PW;
+        Ls[idx] = (r < jb && c < r) ? A[size_t(j + r) * ld + j + c] : T(0);
+    }
+    __syncthreads();
+    const int col = c0 + blockIdx.x * TRSM_THREADS + tid;
+    if (col >= c1) return;
+    T x[PW];
+#pragma unroll
+    for (int i = 0; i < PW; ++i) x[i] = (i < jb) ? A[size_t(j + i) * ld + col] : T(0);
+#pragma unroll
+    for (int k = 0; k < PW - 1; ++k) {
+#pragma unroll
+        for (int i = k + 1; i < PW; ++i) x[i] -= Ls[i * PW + k] * x[k];
+    }
+#pragma unroll
+    for (int i = 1; i < PW; ++i)
+        if (i < jb) A[size_t(j + i) * ld + col] = x[i];
+}
+
+__global__ void iota_kernel(int32_t *p, int n) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = i;
+}
+// perm[rowid[i]] = i  (PermutationMatrix::inverse, permutation_matrix.rs:137-148)
+__global__ void invert_perm_kernel(const int32_t *__restrict__ rowid, int64_t *__restrict__ perm, int n,
+                                   const int32_t *__restrict__ info) {
+    if (*info != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[rowid[i]] = i;
+}
+
+template <typename T>
+int gemm_update(size_t m, size_t k, size_t n, const T *a, size_t lda, const T *b, size_t ldb, T *c, size_t ldc,
+                cudaStream_t st);
+template <>
+int gemm_update<double>(size_t m, size_t k, size_t n, const double *a, size_t lda, const double *b, size_t ldb,
+                        double *c, size_t ldc, cudaStream_t st) {
+    return dgemm_launch(m, k, n, -1.0, a, lda, b, ldb, 1.0, c, ldc, st);
+}
+template <>
+int gemm_update<float>(size_t m, size_t k, size_t n, const float *a, size_t lda, const float *b, size_t ldb,
+                       float *c, size_t ldc, cudaStream_t st) {
+    return sgemm_launch(m, k, n, -1.f, a, lda, b, ldb, 1.f, c, ldc, st);
+}
+
+int g_num_sms = 0;
+
+template <typename T>
+int launch_laswp(T *a, size_t ld, int J, int jb, const int32_t *ipiv, const int32_t *info, int c0a, int c1a,
+                 int c0b, int c1b, int32_t *rowid, cudaStream_t st) {
+    const int ncols = (c1a - c0a) + (c1b - c0b);
+    if (ncols <= 0 && rowid == nullptr) return RLA_OK;
+    // tile <= 128 KB: CW columns x 2*jb rows
+    int CW = int((128 * 1024) / (2 * size_t(jb) * sizeof(T)));
+    CW = CW >= 256 ? 256 : CW >= 128 ? 128 : CW >= 64 ? 64 : 32;
+    const size_t smem = size_t(2) * jb * CW * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+        RLA_CUDA(cudaFuncSetAttribute(laswp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr = true;
+    }
+    int blocks = (ncols + CW - 1) / CW;
+    if (blocks < 1) blocks = 1;
+    laswp_kernel<T><<<blocks, LASWP_THREADS, smem, st>>>(a, ld, J, jb, ipiv, info, c0a, c1a, c0b, c1b, CW, rowid);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+template <typename T>
+int launch_trsm(T *a, size_t ld, int j, int jb, int c0, int c1, const int32_t *info, cudaStream_t st) {
+    if (c1 <= c0 || jb <= 1) return RLA_OK;
+    const int blocks = (c1 - c0 + TRSM_THREADS - 1) / TRSM_THREADS;
+    trsm_unit_lower_kernel<T><<<blocks, TRSM_THREADS, 0, st>>>(a, ld, j, jb, c0, c1, info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+}  // namespace
+
+size_t lu_scratch_bytes() {
+    // cand_abs[2][G] + cand_idx[2][G] + rowbuf[2][G][PW] + diagbuf[2][PW] + barrier word, G <= 256, T <= 8 bytes
+    const size_t G = 256;
+    return 2 * G * 8 + 2 * G * 4 + 2 * G * PW * 8 + 2 * PW * 8 + 256;
+}
+
+template <typename T>
+int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
+    if (n_ > 0x7fffffffull / 2) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    if (n == 0) return RLA_OK;
+    if (g_num_sms == 0) {
+        int dev = 0;
+        RLA_CUDA(cudaGetDevice(&dev));
+        RLA_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+    }
+    // workspace: ipiv[n] + rowid[n] (int32) and the panel scratch
+    if (ws.ipiv_cap < size_t(2) * n) {
+        if (ws.ipiv) RLA_CUDA(cudaFree(ws.ipiv));
+        ws.ipiv = nullptr;
+        ws.ipiv_cap = 0;
+        RLA_CUDA(cudaMalloc(&ws.ipiv, sizeof(int32_t) * 2 * size_t(n)));
+        ws.ipiv_cap = size_t(2) * n;
+    }
+    if (ws.scratch_cap < lu_scratch_bytes()) {
+        if (ws.scratch) RLA_CUDA(cudaFree(ws.scratch));
+        ws.scratch = nullptr;
+        ws.scratch_cap = 0;
+        RLA_CUDA(cudaMalloc(&ws.scratch, lu_scratch_bytes()));
+        ws.scratch_cap = lu_scratch_bytes();
+    }
+    int32_t *ipiv = ws.ipiv;
+    int32_t *rowid = ws.ipiv + n;
+    const size_t GMAX = 256;
+    unsigned char *sp = static_cast<unsigned char *>(ws.scratch);
+    unsigned *bar = reinterpret_cast<unsigned *>(sp);
+    T *cand_abs = reinterpret_cast<T *>(sp + 256);
+    int *cand_idx = reinterpret_cast<int *>(sp + 256 + 2 * GMAX * 8);
+    T *rowbuf = reinterpret_cast<T *>(sp + 256 + 2 * GMAX * 8 + 2 * GMAX * 4);
+    T *diagbuf = reinterpret_cast<T *>(sp + 256 + 2 * GMAX * 8 + 2 * GMAX * 4 + 2 * GMAX * PW * 8);
+    RLA_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, n);
+    RLA_LAUNCHED();
+
+    static bool attr = false;
+    if (!attr) {
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr = true;
+    }
+    unsigned bar_base = 0;
+    for (int J0 = 0; J0 < n; J0 += OUTER_W) {
+        const int w = min(OUTER_W, n - J0);
+        for (int j = J0; j < J0 + w; j += PW) {
+            const int jb = min(PW, J0 + w - j);
+            const int nrem = n - j;
+            int G = min(g_num_sms, max(1, (nrem + 63) / 64));
+            int R = (nrem + G - 1) / G;
+            size_t smem = size_t(R) * PLDS * sizeof(T);
+            if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
+            {
+                T *a_ = a;
+                size_t ld_ = ld;
+                int n__ = n, J_ = j, jb_ = jb, R_ = R;
+                void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &ipiv, &d_info, &cand_abs, &cand_idx, &rowbuf, &diagbuf, &bar, &bar_base};
+                RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(G), dim3(PANEL_THREADS), args, smem, st));
+                note_launch();
+                bar_base += unsigned(G) * unsigned(jb);
+            }
+            // interchanges inside the outer block, then U12 and the Schur update inside the block
+            RLA_TRY(launch_laswp<T>(a, ld, j, jb, ipiv, d_info, J0, j, j + jb, J0 + w, nullptr, st));
+            if (j + jb < J0 + w) {
+                RLA_TRY(launch_trsm<T>(a, ld, j, jb, j + jb, J0 + w, d_info, st));
+                if (j + jb < n)
+                    RLA_TRY(gemm_update<T>(size_t(n - j - jb), size_t(jb), size_t(J0 + w - j - jb),
+                                           a + size_t(j + jb) * ld + j, ld, a + size_t(j) * ld + j + jb, ld,
+                                           a + size_t(j + jb) * ld + j + jb, ld, st));
+            }
+        }
+        // interchanges of the whole outer block applied left and right of it (+ the row-origin vector)
+        RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, rowid, st));
+        if (J0 + w < n) {
+            // U12 = L11^-1 A12 by blocks of PW rows, then A22 -= L21 U12 (k = w)
+            for (int kb = 0; kb < w; kb += PW) {
+                const int jb = min(PW, w - kb);
+                RLA_TRY(launch_trsm<T>(a, ld, J0 + kb, jb, J0 + w, n, d_info, st));
+                if (kb + jb < w)
+                    RLA_TRY(gemm_update<T>(size_t(w - kb - jb), size_t(jb), size_t(n - J0 - w),
+                                           a + size_t(J0 + kb + jb) * ld + J0 + kb, ld,
+                                           a + size_t(J0 + kb) * ld + J0 + w, ld,
+                                           a + size_t(J0 + kb + jb) * ld + J0 + w, ld, st));
+            }
+            RLA_TRY(gemm_update<T>(size_t(n - J0 - w), size_t(w), size_t(n - J0 - w), a + size_t(J0 + w) * ld + J0, ld,
+                                   a + size_t(J0) * ld + J0 + w, ld, a + size_t(J0 + w) * ld + J0 + w, ld, st));
+        }
+    }
+    invert_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, d_perm, n, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
+template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
+
+}  // namespace rla

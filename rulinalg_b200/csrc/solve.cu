@@ -1,0 +1,268 @@
+// solve.cu -- K5 (solve side): x = U^-1 L^-1 P b for a packed PartialPivLu factorisation.
+//
+// Replaces the body of PartialPivLu::solve (src/matrix/decomposition/lu.rs:231-244):
+//   P b            permute_vector_into_buffer (permutation_matrix.rs:369-382): buf[perm[i]] = b[i]
+//   L y = P b      lu_forward_substitution (lu.rs:624-642): unit diagonal, no singularity check
+//   U x = y        back_substitution (src/matrix/mod.rs:318-357): |u_ii| < eps -> DivByZero
+//
+// Two paths:
+//   n <= 64  : getrs_small_kernel, one warp, reproduces the reference's summation ORDER exactly
+//              (sequential fold for L; utils::dot's 8 partial sums + tail for U, src/utils.rs:20-51)
+//              with unfused multiply/add, so small systems are bit-identical to the reference.
+//   n  > 64  : trsv_kernel, HBM-bound blocked substitution.  Block rows of 64; a CTA per block row
+//              (ordered by an atomic ticket so dependencies always point at already-started CTAs)
+//              streams its row panel with 16-byte loads as soon as the x blocks it needs are
+//              published (monotonic `done` counter, release/acquire through __threadfence), keeps 8
+//              row accumulators per lane, then warp 0 solves the 64x64 diagonal block with shuffles.
+//              Summation order differs from the reference => tolerance-based parity.
+#include <cfloat>
+
+#include "common.cuh"
+
+namespace rla {
+namespace {
+
+template <typename T> struct EpsS;
+template <> struct EpsS<double> { static __device__ __forceinline__ double v() { return DBL_EPSILON; } };
+template <> struct EpsS<float> { static __device__ __forceinline__ float v() { return FLT_EPSILON; } };
+
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ float add_rn(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ double div_rn(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, b); }
+
+constexpr int SMALL_N = 64;
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+getrs_small_kernel(int n, const T *__restrict__ lu, size_t ld, const int64_t *__restrict__ perm, T *__restrict__ b,
+                   int32_t *__restrict__ info) {
+    __shared__ T x[SMALL_N];
+    __shared__ T m[SMALL_N * (SMALL_N + 1)];
+    const int lane = threadIdx.x;
+    for (int idx = lane; idx < n * n; idx += 32) {
+        const int r = idx / n, c = idx - r * n;
+        m[r * (SMALL_N + 1) + c] = lu[size_t(r) * ld + c];
+    }
+    for (int i = lane; i < n; i += 32) x[int(perm[i])] = b[i];
+    __syncwarp();
+    // forward: column sweep; each row's sum grows in ascending k exactly like the reference fold
+    T sum0 = T(0), sum1 = T(0);
+    for (int k = 0; k < n; ++k) {
+        if (k > 0 && lane == (k & 31)) {
+            const T s = (k < 32) ? sum0 : sum1;
+            x[k] = sub_rn(x[k], s);
+        }
+        __syncwarp();
+        const T xk = x[k];
+        const int ra = lane, rb = lane + 32;
+        if (ra > k && ra < n) sum0 = add_rn(sum0, mul_rn(m[ra * (SMALL_N + 1) + k], xk));
+        if (rb > k && rb < n) sum1 = add_rn(sum1, mul_rn(m[rb * (SMALL_N + 1) + k], xk));
+    }
+    __syncwarp();
+    // backward: utils::dot order (8 partial sums over full groups of 8, pairwise combine, scalar tail)
+    bool bad = false;
+    for (int i = n - 1; i >= 0; --i) {
+        const T div = m[i * (SMALL_N + 1) + i];
+        if (fabs(div) < EpsS<T>::v()) { bad = true; if (lane == 0) *info = i + 1; break; }
+        const int len = n - i - 1;
+        const int groups = len >> 3;
+        T p = T(0);
+        if (lane < 8)
+            for (int t = 0; t < groups; ++t) {
+                const int j = i + 1 + 8 * t + lane;
+                p = add_rn(p, mul_rn(m[i * (SMALL_N + 1) + j], x[j]));
+            }
+        T pq[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) pq[q] = __shfl_sync(0xffffffffu, p, q);
+        if (lane == 0) {
+            T s = T(0);
+            s = add_rn(add_rn(s, pq[0]), pq[4]);
+            s = add_rn(add_rn(s, pq[1]), pq[5]);
+            s = add_rn(add_rn(s, pq[2]), pq[6]);
+            s = add_rn(add_rn(s, pq[3]), pq[7]);
+            for (int j = i + 1 + 8 * groups; j < n; ++j) s = add_rn(s, mul_rn(m[i * (SMALL_N + 1) + j], x[j]));
+            x[i] = div_rn(sub_rn(x[i], s), div);
+        }
+        __syncwarp();
+    }
+    if (!bad)
+        for (int i = lane; i < n; i += 32) b[i] = x[i];
+}
+
+// out[perm[i]] = in[i]
+template <typename T>
+__global__ void permute_vector_kernel(int n, const int64_t *__restrict__ perm, const T *__restrict__ in,
+                                      T *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[perm[i]] = in[i];
+}
+template <typename T>
+__global__ void copy_if_ok_kernel(int n, const T *__restrict__ in, T *__restrict__ out, const int32_t *__restrict__ info) {
+    if (*info != 0) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = in[i];
+}
+
+constexpr int TB = 64;
+constexpr int TRSV_THREADS = 256;
+
+template <typename T> struct Vec2;
+template <> struct Vec2<double> { using type = double2; };
+template <> struct Vec2<float> { using type = float2; };
+
+// sync words: [0] ticket, [1] done
+template <typename T, bool LOWER>
+__global__ void __launch_bounds__(TRSV_THREADS, 2)
+trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int32_t *__restrict__ info) {
+    using V2 = typename Vec2<T>::type;
+    __shared__ T diag[TB * (TB + 1)];
+    __shared__ T rsum[TB];
+    __shared__ int sh_bid;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nblk = (n + TB - 1) / TB;
+    if (tid == 0) sh_bid = atomicAdd(&sync[0], 1);
+    __syncthreads();
+    const int ord = sh_bid;                       // 0,1,2,... in start order
+    const int I = LOWER ? ord : nblk - 1 - ord;   // my block row
+    const int row0 = I * TB;
+    volatile int32_t *done = sync + 1;
+
+    // prefetch the diagonal block (identity outside the matrix)
+    for (int idx = tid; idx < TB * TB; idx += TRSV_THREADS) {
+        const int r = idx / TB, c = idx - r * TB;
+        T v = (r == c) ? T(1) : T(0);
+        if (row0 + r < n && row0 + c < n) v = lu[size_t(row0 + r) * ld + row0 + c];
+        diag[r * (TB + 1) + c] = v;
+    }
+
+    const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(lu) & (2 * sizeof(T) - 1)) == 0);
+    T acc[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc[q] = T(0);
+    const int nd = LOWER ? I : nblk - 1 - I;      // number of dependency blocks
+    int seen = 0;                                 // cached `done`
+    V2 lcur[8];
+    auto load_tiles = [&](int Jb, V2 *dst) {
+        const int col = Jb * TB + 2 * lane;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            const int row = row0 + warp * 8 + q;
+            V2 v;
+            v.x = T(0);
+            v.y = T(0);
+            if (row < n) {
+                const T *p = lu + size_t(row) * ld + col;
+                if (vec_ok && col + 1 < n) {
+                    v = *reinterpret_cast<const V2 *>(p);
+                } else {
+                    if (col < n) v.x = p[0];
+                    if (col + 1 < n) v.y = p[1];
+                }
+            }
+            dst[q] = v;
+        }
+    };
+    if (nd > 0) load_tiles(LOWER ? 0 : nblk - 1, lcur);
+    for (int t = 0; t < nd; ++t) {
+        const int Jb = LOWER ? t : nblk - 1 - t;
+        if (seen < t + 1) {
+            if (lane == 0) {
+                int s;
+                while ((s = *done) < t + 1) {
+                }
+                seen = s;
+            }
+            seen = __shfl_sync(0xffffffffu, seen, 0);
+            __threadfence();
+        }
+        const int col = Jb * TB + 2 * lane;
+        T x0 = T(0), x1 = T(0);
+        if (col < n) x0 = __ldcg(x + col);
+        if (col + 1 < n) x1 = __ldcg(x + col + 1);
+        V2 lnext[8];
+        if (t + 1 < nd) load_tiles(LOWER ? t + 1 : nblk - 2 - t, lnext);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc[q] += lcur[q].x * x0 + lcur[q].y * x1;
+        if (t + 1 < nd) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) lcur[q] = lnext[q];
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        T v = acc[q];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == 0) rsum[warp * 8 + q] = v;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        // rows lane and lane+32 of the block
+        const int ra = lane, rb = lane + 32;
+        T va = (row0 + ra < n) ? sub_rn(__ldcg(x + row0 + ra), rsum[ra]) : T(0);
+        T vb = (row0 + rb < n) ? sub_rn(__ldcg(x + row0 + rb), rsum[rb]) : T(0);
+        if (LOWER) {
+            for (int k = 0; k < TB; ++k) {
+                const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
+                if (ra > k) va -= diag[ra * (TB + 1) + k] * xk;
+                if (rb > k) vb -= diag[rb * (TB + 1) + k] * xk;
+            }
+        } else {
+            for (int k = TB - 1; k >= 0; --k) {
+                if (lane == (k & 31)) {
+                    const T d = diag[k * (TB + 1) + k];
+                    if (fabs(d) < EpsS<T>::v()) atomicCAS(info, 0, row0 + k + 1);   // mod.rs:333-336
+                    if (k < 32) va = div_rn(va, d); else vb = div_rn(vb, d);
+                }
+                const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
+                if (ra < k) va -= diag[ra * (TB + 1) + k] * xk;
+                if (rb < k) vb -= diag[rb * (TB + 1) + k] * xk;
+            }
+        }
+        if (row0 + ra < n) x[row0 + ra] = va;
+        if (row0 + rb < n) x[row0 + rb] = vb;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) atomicAdd(&sync[1], 1);    // blocks complete in dependency order => counter == #done
+    }
+}
+
+}  // namespace
+
+template <typename T>
+int getrs_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *d_tmp, int32_t *d_info,
+                 int32_t *d_sync, cudaStream_t st) {
+    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    if (n == 0) return RLA_OK;
+    if (n <= SMALL_N) {
+        getrs_small_kernel<T><<<1, 32, 0, st>>>(n, lu, ld, d_perm, d_b, d_info);
+        RLA_LAUNCHED();
+        return RLA_OK;
+    }
+    const int nblk = (n + TB - 1) / TB;
+    permute_vector_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, d_perm, d_b, d_tmp);
+    RLA_LAUNCHED();
+    RLA_CUDA(cudaMemsetAsync(d_sync, 0, 4 * sizeof(int32_t), st));
+    trsv_kernel<T, true><<<nblk, TRSV_THREADS, 0, st>>>(n, lu, ld, d_tmp, d_sync, d_info);
+    RLA_LAUNCHED();
+    trsv_kernel<T, false><<<nblk, TRSV_THREADS, 0, st>>>(n, lu, ld, d_tmp, d_sync + 2, d_info);
+    RLA_LAUNCHED();
+    copy_if_ok_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, d_tmp, d_b, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+template int getrs_launch<double>(size_t, const double *, size_t, const int64_t *, double *, double *, int32_t *,
+                                  int32_t *, cudaStream_t);
+template int getrs_launch<float>(size_t, const float *, size_t, const int64_t *, float *, float *, int32_t *,
+                                 int32_t *, cudaStream_t);
+
+}  // namespace rla

@@ -1,0 +1,404 @@
+"""Parity tests proper: the CUDA path (through the C ABI / the Matrix mirror) against the CPU oracle
+and the reference's known-answer vectors.  Run on the B200 box:  pytest -m gpu.
+
+Stated tolerances (DESIGN.md "Parity"):
+  GEMM   hard gate  |c_gpu - c_ref| <= 2*gamma_k*(|A||B|)_ij, gamma_k = k*u/(1-k*u)   (any order)
+         asserted   assert_matrix_eq!(gpu, ref, comp = ulp, tol = ceil(4*sqrt(k)))  on U[0,1) data
+         mixed sign comp = float, eps = 2*gamma_k*max(|A||B|), ulp = ceil(4*sqrt(k))
+         KATs       comp = exact
+  LU     n <= 64 (one panel): factors and perm BIT-EXACT vs the oracle
+         n  > 64: identical pivot sequence, P^-1 L U vs A  comp = abs, tol = 8*n*u*rho*max|A|
+  solve  n <= 64: BIT-EXACT; larger: scaled residual <= 16 and relative error vs oracle
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import pytest
+
+from tests.golden import reference_kats as K
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def rla():
+    import rulinalg_b200 as r
+    st = r.lib().rla_init(0)
+    assert st == 0, r.lib().rla_strerror(st)
+    return r
+
+
+def U(dtype):
+    return 2.0 ** -53 if np.dtype(dtype) == np.float64 else 2.0 ** -24
+
+
+def gamma(k, dtype):
+    u = U(dtype)
+    return k * u / (1 - k * u)
+
+
+def M(rla, x, dtype=np.float64):
+    return rla.Matrix.from_numpy(np.array(x, dtype=dtype))
+
+
+def gpu_gemm_host(rla, a, b, alpha=1.0, beta=0.0, c=None):
+    """straight through the host-pointer C ABI with arbitrary numpy strides"""
+    m, k = a.shape
+    n = b.shape[1]
+    it = a.dtype.itemsize
+    if c is None:
+        c = np.full((m, n), np.nan, dtype=a.dtype)     # poison: beta == 0 must never read C
+    fn = rla.lib().rla_dgemm if a.dtype == np.float64 else rla.lib().rla_sgemm
+    st = fn(m, k, n, alpha, a.ctypes.data, a.strides[0] // it, a.strides[1] // it,
+            b.ctypes.data, b.strides[0] // it, b.strides[1] // it, beta,
+            c.ctypes.data, c.strides[0] // it, c.strides[1] // it)
+    assert rla.check(st) == 0
+    return c
+
+
+def gpu_gemm_dev(rla, a, b, alpha=1.0, beta=0.0, c=None, lda=None, ldb=None, ldc=None):
+    """device-resident twin with explicit leading dimensions (odd ld exercises the 8-byte path)"""
+    m, k = a.shape
+    n = b.shape[1]
+    dt = a.dtype
+    lda = lda or max(k, 1)
+    ldb = ldb or n
+    ldc = ldc or n
+    ap = np.zeros((m, lda), dt); ap[:, :k] = a
+    bp = np.zeros((max(k, 1), ldb), dt); bp[:k, :n] = b
+    cp = np.full((m, ldc), np.nan, dt)
+    if c is not None:
+        cp[:, :n] = c
+    da, db, dc = (rla.DeviceBuffer(max(x.nbytes, 16)) for x in (ap, bp, cp))
+    da.upload(ap); db.upload(bp); dc.upload(cp)
+    fn = rla.lib().rla_dgemm_dev if dt == np.float64 else rla.lib().rla_sgemm_dev
+    assert rla.check(fn(m, k, n, alpha, da.ptr, lda, db.ptr, ldb, beta, dc.ptr, ldc, None)) == 0
+    out = dc.download((m, ldc), dt)
+    for d in (da, db, dc):
+        d.free()
+    return out[:, :n]
+
+
+def check_gemm(oracle, a, b, got, positive):
+    k = a.shape[1]
+    ref = oracle.gemm(a, b)
+    bound = 2 * gamma(max(k, 1), a.dtype) * (np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64))
+    err = np.abs(got.astype(np.float64) - ref.astype(np.float64))
+    assert np.all(err <= bound + 0.0), f"Higham gate violated: max err {err.max()} bound {bound.max()}"
+    ulp_tol = math.ceil(4 * math.sqrt(max(k, 1)))
+    if positive:
+        info = oracle.assert_matrix_eq(got, ref, comp="ulp", tol=ulp_tol)
+    else:
+        oracle.assert_matrix_eq(got, ref, comp="float", eps=float(bound.max()), ulp=ulp_tol)
+        info = {}
+    return info
+
+
+# ============================================================================ GEMM
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_matrix_mul_kat(rla, oracle, dtype):
+    # src/matrix/mat_mul.rs:293-341 through the Matrix mirror (exact)
+    a = M(rla, K.GEMM_3x2_2x3["a"], dtype)
+    b = M(rla, K.GEMM_3x2_2x3["b"], dtype)
+    c = a * b
+    assert (c.rows(), c.cols()) == (3, 3)
+    oracle.assert_matrix_eq(c.to_numpy(), np.array(K.GEMM_3x2_2x3["c"], dtype), comp="exact")
+
+
+def test_mul_slice_kats(rla, oracle):
+    # src/matrix/mat_mul.rs:368-412: operands with row_stride != cols
+    g = K.GEMM_SLICE_BASIC
+    c = M(rla, g["parent"])
+    d = rla.MatrixSlice.from_matrix(c, list(g["start"]), g["rows"], g["cols"])
+    assert d.row_stride() == 3
+    assert (d * rla.Matrix.ones(2, 2)).into_vec() == [4.0] * 4
+    assert (d * d).into_vec() == [8.0] * 4
+    g = K.GEMM_SLICE_UNEVEN
+    d = rla.MatrixSlice.from_matrix(M(rla, g["parent"]), [0, 0], 2, 2)
+    e = d * M(rla, g["rhs"])
+    oracle.assert_matrix_eq(e.to_numpy(), np.array(g["c"]), comp="exact")
+
+
+def test_mul_dimension_mismatch_panics(rla):
+    # mat_mul.rs:21
+    with pytest.raises(rla.Panic, match="Matrix dimensions do not agree."):
+        rla.Matrix.ones(2, 3) * rla.Matrix.ones(2, 3)
+
+
+SHAPES = [(1, 1, 1), (3, 2, 3), (17, 5, 9), (64, 64, 64), (128, 128, 128), (129, 130, 131), (200, 333, 77),
+          (255, 1000, 257), (512, 512, 512), (1024, 1024, 1024), (4096, 256, 256)]
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gemm_vs_oracle_positive(rla, oracle, dtype, shape):
+    m, k, n = shape
+    a = oracle.fill_uniform((m, k), 12, dtype)
+    b = oracle.fill_uniform((k, n), 2049, dtype)
+    got = (rla.Matrix.from_numpy(a) * rla.Matrix.from_numpy(b)).to_numpy()
+    check_gemm(oracle, a, b, got, positive=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("shape", [(129, 130, 131), (512, 512, 512), (300, 2000, 100)])
+def test_gemm_vs_oracle_mixed_sign(rla, oracle, dtype, shape):
+    m, k, n = shape
+    a = oracle.fill_uniform((m, k), 12, dtype, lo=-1.0, scale=2.0)
+    b = oracle.fill_uniform((k, n), 2049, dtype, lo=-1.0, scale=2.0)
+    got = gpu_gemm_host(rla, a, b)
+    check_gemm(oracle, a, b, got, positive=False)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gemm_strides_alpha_beta(rla, oracle, dtype):
+    m, k, n = 150, 70, 90
+    big_a = oracle.fill_uniform((m, k + 7), 1, dtype)
+    big_b = oracle.fill_uniform((k, n + 3), 2, dtype)
+    a, b = big_a[:, 2:2 + k], big_b[:, 1:1 + n]                 # row_stride > cols, offset start
+    c0 = oracle.fill_uniform((m, n), 3, dtype)
+    ref = oracle.gemm(a, b, alpha=0.5, beta=2.0, c=c0.copy())
+    got = gpu_gemm_host(rla, a, b, alpha=0.5, beta=2.0, c=c0.copy())
+    tol = 4 * gamma(k + 2, dtype) * (0.5 * np.abs(a).astype(np.float64) @ np.abs(b).astype(np.float64) + 2 * np.abs(c0))
+    assert np.all(np.abs(got.astype(np.float64) - ref) <= tol)
+    # general strides: transposed (column-major) operands and a transposed output
+    at = np.ascontiguousarray(a.T).T
+    bt = np.ascontiguousarray(b.T).T
+    ct = np.full((n, m), np.nan, dtype).T
+    got2 = gpu_gemm_host(rla, at, bt, c=ct)
+    check_gemm(oracle, np.ascontiguousarray(a), np.ascontiguousarray(b), np.ascontiguousarray(got2), positive=True)
+    # negative row stride on an input
+    ar = np.ascontiguousarray(a)[::-1]
+    got3 = gpu_gemm_host(rla, ar, np.ascontiguousarray(b))
+    check_gemm(oracle, np.ascontiguousarray(ar), np.ascontiguousarray(b), got3, positive=True)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gemm_device_twin_odd_ld(rla, oracle, dtype):
+    # odd leading dimensions => unaligned (8-byte / 4-byte cp.async) kernel variant
+    m, k, n = 131, 67, 129
+    a = oracle.fill_uniform((m, k), 5, dtype)
+    b = oracle.fill_uniform((k, n), 6, dtype)
+    got = gpu_gemm_dev(rla, a, b, lda=k + 2 if k % 2 else k + 1, ldb=n + 2, ldc=n + 4)
+    check_gemm(oracle, a, b, got, positive=True)
+    got = gpu_gemm_dev(rla, a, b, lda=k + 4 - k % 4 + 4, ldb=n + 4 - n % 4, ldc=n + 4 - n % 4)   # aligned variant
+    check_gemm(oracle, a, b, got, positive=True)
+    # beta = 1 accumulation (the LU trailing-update form)
+    c0 = oracle.fill_uniform((m, n), 7, dtype)
+    got = gpu_gemm_dev(rla, a, b, alpha=-1.0, beta=1.0, c=c0)
+    ref = c0.astype(np.float64) - a.astype(np.float64) @ b.astype(np.float64)
+    assert np.max(np.abs(got - ref)) <= 4 * gamma(k + 1, dtype) * (k + 1)
+
+
+def test_gemm_degenerate(rla):
+    # m*n == 0 -> no-op; k == 0 with beta == 0 -> zero fill
+    assert (rla.Matrix.zeros(0, 3) * rla.Matrix.zeros(3, 4)).rows() == 0
+    c = rla.Matrix.zeros(2, 0) * rla.Matrix.zeros(0, 3)
+    assert (c.rows(), c.cols()) == (2, 3) and np.all(c.to_numpy() == 0.0)
+    a = np.zeros((2, 0)); b = np.zeros((0, 3))
+    c0 = np.full((2, 3), 3.0)
+    got = gpu_gemm_host(rla, a, b, alpha=1.0, beta=0.5, c=c0.copy())
+    assert np.all(got == 1.5)
+
+
+def test_gemm_linearity_and_freivalds_full_size(rla, oracle):
+    # BASELINE size (n = 8192 f64) through size-independent properties: Freivalds C x == A (B x) within
+    # the Higham bound, plus 2048 sampled entries against extended-precision dots.
+    n = 8192
+    l = rla.lib()
+    bufs = [rla.DeviceBuffer(n * n * 8) for _ in range(3)]
+    assert l.rla_fill_uniform_f64_dev(bufs[0].ptr, n, n, n, 12, 0, 0.0, 1.0, None) == 0
+    assert l.rla_fill_uniform_f64_dev(bufs[1].ptr, n, n, n, 2049, 0, 0.0, 1.0, None) == 0
+    assert l.rla_dgemm_dev(n, n, n, 1.0, bufs[0].ptr, n, bufs[1].ptr, n, 0.0, bufs[2].ptr, n, None) == 0
+    c = bufs[2].download((n, n), np.float64)
+    a = oracle.fill_uniform((n, n), 12)
+    b = oracle.fill_uniform((n, n), 2049)
+    # the device generator is bit-identical to the oracle's
+    a_dev = bufs[0].download((n, n), np.float64)
+    assert np.array_equal(a_dev, a)
+    for d in bufs:
+        d.free()
+    x = oracle.fill_uniform((n,), 4000)
+    lhs = c @ x
+    rhs = a @ (b @ x)
+    bound = 3 * gamma(n, np.float64) * (np.abs(a) @ (np.abs(b) @ np.abs(x)))
+    assert np.all(np.abs(lhs - rhs) <= bound)
+    rng = np.random.default_rng(7)
+    ii = rng.integers(0, n, 2048); jj = rng.integers(0, n, 2048)
+    truth, absd = oracle.gemm_truth_samples(a, b, ii, jj)
+    assert np.all(np.abs(c[ii, jj] - truth) <= gamma(n, np.float64) * absd)
+    rel = np.max(np.abs(c[ii, jj] - truth) / np.abs(truth))
+    assert rel < 8 * math.sqrt(n) * U(np.float64), rel
+
+
+# ============================================================================ LU
+def decompose(rla, a):
+    return rla.PartialPivLu.decompose(rla.Matrix.from_numpy(a))
+
+
+def test_lu_kats_through_api(rla, oracle):
+    # tests/mat/mod.rs:100-170, lu.rs:775-793: exact factors and reconstructions, comp = float
+    g = K.LU_EXACT_3x3
+    f = decompose(rla, np.array(g["a"])).unpack()
+    oracle.assert_matrix_eq(f.l.to_numpy(), np.array(g["l"]), comp="float")
+    oracle.assert_matrix_eq(f.u.to_numpy(), np.array(g["u"]), comp="float")
+    oracle.assert_matrix_eq(f.p.as_matrix().to_numpy(), np.array(g["p"]), comp="float")
+    for a in K.LU_RECONSTRUCT:
+        a = np.array(a)
+        f = decompose(rla, a).unpack()
+        k = f.p.inverse() * (f.l * f.u)
+        oracle.assert_matrix_eq(k.to_numpy(), a, comp="float")
+        assert oracle.is_lower_triangular(f.l.to_numpy()) and oracle.is_upper_triangular(f.u.to_numpy())
+
+
+def test_lu_inverse_det_solve_kats(rla, oracle):
+    # lu.rs:796-862, impl_mat.rs:648-693, tests/mat/mod.rs:4-26
+    g = K.LU_INVERSE_4x4
+    oracle.assert_matrix_eq(decompose(rla, np.array(g["a"])).inverse().to_numpy(), np.array(g["inv"]), comp="float")
+    g = K.LU_DET_4x4
+    oracle.assert_matrix_eq(np.array([decompose(rla, np.array(g["a"])).det()]), np.array([g["det"]]), comp="float")
+    g = K.LU_SOLVE_4x4
+    y = decompose(rla, np.array(g["a"])).solve(rla.Vector(g["b"]))
+    oracle.assert_matrix_eq(y.data(), np.array(g["x"]), comp="ulp", tol=g["ulp_tol"])
+    g = K.SOLVE_LAPLACIAN
+    c = M(rla, g["a"]).solve(rla.Vector(g["b"]))
+    oracle.assert_matrix_eq(c.data(), np.array(g["x"]), comp="abs", tol=g["abs_tol"])
+    g = K.SOLVE_2x2
+    x = M(rla, g["a"]).solve(rla.Vector(g["b"]))
+    assert x.size() == 2 and x[0] == 1.0 and x[1] == 2.0
+    g = K.SOLVE_IDENTITY
+    y = rla.PartialPivLu.decompose(rla.Matrix.identity(g["n"])).solve(rla.Vector(g["b"]))
+    oracle.assert_matrix_eq(y.data(), np.array(g["b"]), comp="float")
+    # Matrix::det incl. the special cases and singular -> 0 (impl_mat.rs:648-678)
+    assert M(rla, [[2., 3.], [1., 2.]]).det() == 1.0
+    assert M(rla, [[1., 2., 3.], [4., 5., 6.], [7., 8., 9.]]).det() == 0.0
+    oracle.assert_matrix_eq(np.array([M(rla, K.DET_5x5["a"]).det()]), np.array([K.DET_5x5["det"]]), comp="float")
+    assert M(rla, K.LU_SINGULAR).det() == 0.0
+
+
+def test_lu_errors_and_panics(rla):
+    # lu.rs:749-772: non-square panics, singular -> ErrorKind::DivByZero
+    with pytest.raises(rla.Panic):
+        rla.PartialPivLu.decompose(rla.Matrix.ones(2, 3))
+    with pytest.raises(rla.Error) as ei:
+        decompose(rla, np.array(K.LU_SINGULAR))
+    assert ei.value.kind() == rla.ErrorKind.DivByZero
+    lu = decompose(rla, np.eye(3))
+    with pytest.raises(rla.Panic):
+        lu.solve(rla.Vector([1.0, 2.0]))
+    # back_substitution's |u_ii| < eps check (mod.rs:333-336) through a hand-made factorisation
+    bad = rla.PartialPivLu(M(rla, [[1.0, 2.0], [0.5, 1e-17]]), rla.PermutationMatrix.identity(2))
+    with pytest.raises(rla.Error) as ei:
+        bad.solve(rla.Vector([1.0, 1.0]))
+    assert ei.value.kind() == rla.ErrorKind.DivByZero
+    # empty matrix
+    e = rla.PartialPivLu.decompose(rla.Matrix.zeros(0, 0))
+    assert e.solve(rla.Vector([])).size() == 0 and e.det() == 1.0
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 2, 3, 7, 16, 31, 33, 63, 64])
+def test_lu_bit_exact_within_one_panel(rla, oracle, dtype, n):
+    # F13: n <= panel width => factors, perm and solve bit-identical to the reference restatement
+    for seed, lo, scale in ((12, 0.0, 1.0), (99, -1.0, 2.0)):
+        a = oracle.fill_uniform((n, n), seed, dtype, lo=lo, scale=scale)
+        ref_lu, ref_perm = oracle.lu_decompose(a)
+        f = decompose(rla, a)
+        assert f.p.perm().tolist() == ref_perm.tolist()
+        oracle.assert_matrix_eq(f.lu.to_numpy(), ref_lu, comp="exact")
+        b = oracle.fill_uniform((n,), 4000, dtype)
+        x = f.solve(rla.Vector(b)).data()
+        oracle.assert_matrix_eq(x, oracle.lu_solve(ref_lu, ref_perm, b), comp="exact")
+
+
+def test_lu_pivot_rule_ties_and_nan(rla, oracle):
+    # first row attaining the max wins (lu.rs:173-178); ties across CTAs of the panel kernel too
+    n = 200
+    a = oracle.fill_uniform((n, n), 5, lo=-0.5, scale=1.0)
+    a[[3, 77, 150], 0] = 0.75          # three-way tie in column 0; rows live in different CTAs
+    a[150, 0] = -0.75
+    f = decompose(rla, a)
+    ref_lu, ref_perm = oracle.lu_decompose(a)
+    assert f.p.perm()[3] == 0 and ref_perm[3] == 0
+    assert f.p.perm().tolist() == ref_perm.tolist()
+    # a NaN below the diagonal never wins a comparison
+    a = oracle.fill_uniform((8, 8), 6)
+    a[5, 0] = np.nan
+    ref_lu, ref_perm = oracle.lu_decompose(a)
+    f = decompose(rla, a)
+    assert f.p.perm().tolist() == ref_perm.tolist()
+    assert np.array_equal(f.lu.to_numpy(), ref_lu, equal_nan=True)
+
+
+def lu_checks(rla, oracle, a, f, ref=None):
+    n = a.shape[0]
+    dt = a.dtype
+    lu = f.lu.to_numpy().astype(np.float64)
+    perm = f.p.perm()
+    assert sorted(perm.tolist()) == list(range(n))
+    l = np.tril(lu, -1) + np.eye(n)
+    u = np.triu(lu)
+    assert np.max(np.abs(np.tril(lu, -1))) <= 1.0                      # partial pivoting bound
+    rho = max(1.0, np.max(np.abs(u)) / np.max(np.abs(a)))              # observed growth
+    recon = np.empty_like(lu)
+    recon[:] = (l @ u)[perm.astype(np.int64)]                          # P^-1 (L U): row i of A sits at perm[i]
+    tol = 8 * n * U(dt) * rho * float(np.max(np.abs(a)))
+    oracle.assert_matrix_eq(recon, a.astype(np.float64), comp="abs", tol=tol)
+    if ref is not None:
+        ref_lu, ref_perm = ref
+        assert perm.tolist() == ref_perm.tolist(), "pivot sequence differs from the reference restatement"
+        return oracle.max_ulp(f.lu.to_numpy(), ref_lu)
+    return None
+
+
+@pytest.mark.parametrize("dtype,n", [(np.float64, 65), (np.float64, 100), (np.float64, 128), (np.float64, 129),
+                                     (np.float64, 256), (np.float64, 257), (np.float64, 500), (np.float64, 1024),
+                                     (np.float64, 2048), (np.float32, 100), (np.float32, 300), (np.float32, 1024)])
+def test_lu_vs_oracle_blocked(rla, oracle, dtype, n):
+    a = oracle.fill_uniform((n, n), 12, dtype)
+    ref = oracle.lu_decompose(a, fast=True)
+    f = decompose(rla, a)
+    lu_checks(rla, oracle, a, f, ref)
+    # solve parity: HPL-style scaled residual and distance to the oracle solution
+    b = oracle.fill_uniform((n,), 4000, dtype)
+    x = f.solve(rla.Vector(b)).data().astype(np.float64)
+    a64 = a.astype(np.float64)
+    eps = 2 * U(dt)
+    res = np.max(np.abs(a64 @ x - b)) / (np.max(np.sum(np.abs(a64), axis=1)) * np.max(np.abs(x)) * n * eps)
+    assert res <= 16, res
+    x_ref = oracle.lu_solve(ref[0], ref[1], b, fast=True).astype(np.float64)
+    kappa = np.linalg.cond(a64, 1)
+    assert np.max(np.abs(x - x_ref)) / np.max(np.abs(x_ref)) <= 8 * n * U(dt) * kappa
+
+
+def test_lu_diag_dominant_no_pivoting(rla, oracle):
+    n = 300
+    a = oracle.fill_uniform((n, n), 12) + n * np.eye(n)
+    f = decompose(rla, a)
+    assert f.p.perm().tolist() == list(range(n))
+    lu_checks(rla, oracle, a, f, oracle.lu_decompose(a))
+
+
+def test_lu_full_size_properties(rla, oracle):
+    # BASELINE C3: n = 4096 f64 decompose + solve; oracle too slow => residual / backward error only
+    n = 4096
+    a = oracle.fill_uniform((n, n), 12)
+    f = decompose(rla, a)
+    lu_checks(rla, oracle, a, f)
+    b = np.ones(n)                                           # benches/linalg/lu.rs:125,137
+    x = f.solve(rla.Vector(b)).data()
+    eps = 2.0 ** -52
+    res = np.max(np.abs(a @ x - b)) / (np.max(np.sum(np.abs(a), axis=1)) * np.max(np.abs(x)) * n * eps)
+    assert res <= 16, res
+    # repeated solves reuse the device-resident factors (handle path) and agree with rla_dgetrs
+    x2 = np.array(b, copy=True)
+    st = rla.lib().rla_dgetrs(n, f.lu.as_ptr(), f.p.perm().ctypes.data, x2.ctypes.data)
+    assert st == 0 and np.array_equal(x2, x)
+
+
+def test_launch_counter_and_version(rla):
+    l = rla.lib()
+    l.rla_launch_count_reset()
+    _ = rla.Matrix.ones(4, 4) * rla.Matrix.ones(4, 4)
+    assert l.rla_launch_count() >= 1
+    assert b"sm_100a" in l.rla_version()

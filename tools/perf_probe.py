@@ -1,0 +1,94 @@
+"""Quick device-resident perf probe (development tool, not the bench contract): GFLOP/s of the
+DGEMM / SGEMM / LU / solve kernels through the C ABI device twins, CUDA-event timed on torch's stream."""
+import json
+import sys
+import os
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import rulinalg_b200 as rla
+
+
+def timed(fn, reps, warm=2):
+    st = torch.cuda.current_stream()
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(reps):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(st)
+        fn()
+        e1.record(st)
+        e1.synchronize()
+        ts.append(e0.elapsed_time(e1))
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def main():
+    l = rla.lib()
+    assert l.rla_init(0) == 0
+    torch.cuda.set_device(0)
+    s = torch.cuda.current_stream().cuda_stream
+    which = sys.argv[1:] or ["dgemm", "sgemm", "lu", "solve"]
+    out = []
+    if "dgemm" in which or "sgemm" in which:
+        shapes = [(n, n, n) for n in (512, 1024, 2048, 4096, 8192, 16384)] + [(65536, 256, 256), (4096, 32768, 32768), (16384, 256, 16384), (16384, 64, 192)]
+        for name, dt, fn in (("dgemm", torch.float64, l.rla_dgemm_dev), ("sgemm", torch.float32, l.rla_sgemm_dev)):
+            if name not in which:
+                continue
+            for (m, k, n) in shapes:
+                if name == "sgemm" and k == 32768:
+                    continue
+                a = torch.rand(m, k, dtype=dt, device="cuda")
+                b = torch.rand(k, n, dtype=dt, device="cuda")
+                c = torch.empty(m, n, dtype=dt, device="cuda")
+                reps = 3 if m * k * n > 2e11 else 10
+                best, med = timed(lambda: rla.check(fn(m, k, n, 1.0, a.data_ptr(), k, b.data_ptr(), n, 0.0, c.data_ptr(), n, s)), reps)
+                rec = dict(op=name, m=m, k=k, n=n, ms_best=best, ms_med=med, tflops_best=2 * m * k * n / best * 1e-9, tflops_med=2 * m * k * n / med * 1e-9)
+                print(json.dumps(rec), flush=True)
+                out.append(rec)
+                del a, b, c
+    if "lu" in which:
+        for dt, fn, name in ((torch.float64, l.rla_dgetrf_dev, "dgetrf"), (torch.float32, l.rla_sgetrf_dev, "sgetrf")):
+            for n in (256, 1024, 2048, 4096, 8192, 16384, 32768):
+                if name == "sgetrf" and n > 8192:
+                    continue
+                a0 = torch.rand(n, n, dtype=dt, device="cuda")
+                a = torch.empty_like(a0)
+                perm = torch.empty(n, dtype=torch.int64, device="cuda")
+                info = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+                def run():
+                    a.copy_(a0)
+                    rla.check(fn(n, a.data_ptr(), n, perm.data_ptr(), info.data_ptr(), s))
+
+                def copy_only():
+                    a.copy_(a0)
+
+                reps = 2 if n >= 16384 else 5
+                best, med = timed(run, reps, warm=1)
+                cbest, _ = timed(copy_only, reps, warm=1)
+                ms = best - cbest
+                rec = dict(op=name, n=n, ms=ms, tflops=2 / 3 * n ** 3 / ms * 1e-9, info=int(info.item()))
+                print(json.dumps(rec), flush=True)
+                if name == "dgetrf" and n in (4096, 32768):
+                    b = torch.ones(n, dtype=dt, device="cuda")
+                    b0 = b.clone()
+
+                    def solve():
+                        b.copy_(b0)
+                        rla.check(l.rla_dgetrs_dev(n, a.data_ptr(), n, perm.data_ptr(), b.data_ptr(), info.data_ptr(), s))
+
+                    sbest, smed = timed(solve, 5, warm=1)
+                    rec = dict(op="dgetrs", n=n, ms=sbest, gbs=8 * n * n / sbest * 1e-6, info=int(info.item()))
+                    print(json.dumps(rec), flush=True)
+                del a0, a
+                torch.cuda.empty_cache()
+
+
+if __name__ == "__main__":
+    main()
