@@ -90,7 +90,7 @@ RLA_API void rla_lu_free(rla_lu_handle *h);
 /* ---------------------------------------------------------------------------------------
  * Device-resident twins (kernel timing, multi-GPU sharding, LU -> solve reuse).
  * All pointers are device pointers on the current device; `stream` is a cudaStream_t passed
- * as void* (NULL = the library's own per-thread stream).  Calls are asynchronous on that
+ * as void* (NULL = the CUDA legacy default stream, as in the runtime API).  Calls are asynchronous on that
  * stream unless stated.
  * ------------------------------------------------------------------------------------- */
 RLA_API int rla_init(int device);                 /* select device + create context; idempotent      */

@@ -107,7 +107,7 @@ int ensure_ctx(int device = -1) {
     return RLA_OK;
 }
 
-cudaStream_t pick_stream(void *s) { return s ? static_cast<cudaStream_t>(s) : tl_ctx.stream; }
+cudaStream_t pick_stream(void *s) { return static_cast<cudaStream_t>(s); }   // NULL = CUDA legacy default stream
 
 bool is_pinned(const void *p) {
     cudaPointerAttributes at;

@@ -363,6 +363,7 @@ def test_lu_vs_oracle_blocked(rla, oracle, dtype, n):
     b = oracle.fill_uniform((n,), 4000, dtype)
     x = f.solve(rla.Vector(b)).data().astype(np.float64)
     a64 = a.astype(np.float64)
+    dt = a.dtype
     eps = 2 * U(dt)
     res = np.max(np.abs(a64 @ x - b)) / (np.max(np.sum(np.abs(a64), axis=1)) * np.max(np.abs(x)) * n * eps)
     assert res <= 16, res

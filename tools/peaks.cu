@@ -14,6 +14,8 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <algorithm>
 #include <vector>
 
 namespace cg = cooperative_groups;
@@ -121,8 +123,13 @@ static float time_ms(cudaEvent_t a, cudaEvent_t b) {
     return ms;
 }
 
+static bool want(const char *sel, const char *group) { return strcmp(sel, "all") == 0 || strcmp(sel, group) == 0; }
+
 int main(int argc, char **argv) {
+    // usage: peaks <big:0|1> <group: all|pipes|barriers|cublas|cusolver>
     const bool big = argc > 1 && atoi(argv[1]) > 0;
+    const char *sel = argc > 2 ? argv[2] : "all";
+    setvbuf(stdout, nullptr, _IOLBF, 0);
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
     const int sms = prop.multiProcessorCount;
@@ -137,6 +144,7 @@ int main(int argc, char **argv) {
     CK(cudaMalloc(&dout, 1024));
 
     // ---- DMMA peak: sweep warps/SM ------------------------------------------------------
+    if (want(sel, "pipes")) {
     for (int threads : {128, 256, 512, 1024}) {
         const int iters = 20000;
         constexpr int ILP = 8;
@@ -214,8 +222,9 @@ int main(int argc, char **argv) {
         printf("{\"probe\":\"ffma_sustained\",\"seconds\":%.3f,\"tflops\":%.3f}\n", ms * 1e-3, flops / ms * 1e-9);
     }
 
+    }
     // ---- barrier latencies ---------------------------------------------------------------------
-    {
+    if (want(sel, "barriers")) {
         unsigned *counter;
         long long *cycles;
         CK(cudaMalloc(&counter, 4));
@@ -270,9 +279,10 @@ int main(int argc, char **argv) {
     }
 
     // ---- cuBLAS ceilings -------------------------------------------------------------------------
+    if (want(sel, "cublas")) {
     cublasHandle_t h;
     cublasCreate(&h);
-    cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);  // no TF32, no reduced precision
+    cublasSetMathMode(h, CUBLAS_DEFAULT_MATH);  // default math: FP32 SGEMM stays FP32 (TF32 is opt-in)
     for (int n : {1024, 2048, 4096, 8192, 16384}) {
         if (n > 8192 && !big) continue;
         double *a, *b, *c;
@@ -338,7 +348,9 @@ int main(int argc, char **argv) {
         cudaFree(b);
         cudaFree(c);
     }
+    }
     // ---- cuSOLVER getrf ceiling -------------------------------------------------------------------
+    if (want(sel, "cusolver")) {
     cusolverDnHandle_t sh;
     cusolverDnCreate(&sh);
     for (int n : {1024, 4096, 8192, 16384, 32768}) {
@@ -381,6 +393,7 @@ int main(int argc, char **argv) {
         cudaFree(ipiv);
         cudaFree(info);
         cudaFree(work);
+    }
     }
     return 0;
 }
