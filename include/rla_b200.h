@@ -133,6 +133,10 @@ RLA_API int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size
 RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
                              uint64_t offset, float lo, float scale, void *stream);
 
+/* Tuning knobs (development / benchmarking).  "dgemm_cfg": 0 = 128x64 CTA tile, two CTAs per SM
+ * (default); 1 = 128x128 CTA tile, one CTA per SM.  Returns RLA_ERR_INVALID for unknown keys. */
+RLA_API int rla_set_tuning(const char *key, int value);
+
 /* Diagnostics */
 RLA_API const char *rla_strerror(int status);
 RLA_API int rla_last_cuda_error(void);            /* cudaError_t of the last failing CUDA call (per thread) */

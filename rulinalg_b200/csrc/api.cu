@@ -14,6 +14,8 @@
 
 namespace rla {
 
+extern int g_dgemm_cfg;   // dgemm.cu
+
 namespace {
 
 thread_local cudaError_t tl_last_cuda = cudaSuccess;
@@ -461,6 +463,16 @@ int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, ui
                              float scale, void *stream) {
     RLA_TRY(ensure_ctx());
     return fill_uniform_launch<float>(dst, rows, cols, ld, seed, offset, lo, scale, pick_stream(stream));
+}
+
+int rla_set_tuning(const char *key, int value) {
+    if (!key) return RLA_ERR_INVALID;
+    if (strcmp(key, "dgemm_cfg") == 0) {
+        if (value < 0 || value > 1) return RLA_ERR_INVALID;
+        g_dgemm_cfg = value;
+        return RLA_OK;
+    }
+    return RLA_ERR_INVALID;
 }
 
 const char *rla_strerror(int status) {

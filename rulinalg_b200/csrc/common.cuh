@@ -50,6 +50,7 @@ struct LuWorkspace {
     int32_t *ipiv = nullptr;      // [n] pivot row chosen at each column (LAPACK-style, 0-based)
     void *scratch = nullptr;      // panel scratch (candidates, barrier words, row buffers)
     size_t ipiv_cap = 0, scratch_cap = 0;
+    unsigned tag = 0;             // next free packet tag (unique per panel column while scratch lives)
 };
 template <typename T>
 int getrf_launch(size_t n, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws,

@@ -5,93 +5,129 @@
 // trailing update of the blocked LU (lu.cu).
 //
 // Design (DESIGN.md "K1"):
-//   CTA tile 128x128, k-slab 16, 256 threads = 8 warps as 2(m) x 4(n), warp tile 64x32 =
-//   8x4 DMMA fragments -> 64 accumulator doubles (128 registers) per thread.  A (k contiguous)
-//   and B (n contiguous) slabs are staged global->shared with 16-byte cp.async (LDGSTS) in a
-//   4-stage ring, one __syncthreads per slab.  Shared rows are padded by 4 doubles so that the
-//   8-byte fragment loads of a half-warp hit 32 distinct banks for both operands:
-//     A frag  As[row=g][k=t]   : word = row*40 + 2k   -> bank 8g+2t (+0/1)
-//     B frag  Bs[k=t][col=g]   : word = k*264 + 2col  -> bank 8t+2g (+0/1)
-//   Tiles are rasterised in bands of 16 tile-rows so that the 148 co-resident CTAs share A and B
-//   slabs through the 126 MB L2 (HBM traffic ~ compulsory; see profiles/).
-//   beta == 0 never reads C (mat_mul.rs:52-55 hands over uninitialised memory).
+//   Warp tile 64x32 = 8x4 DMMA fragments -> 64 accumulator doubles (128 registers) per thread.
+//   Two CTA shapes, same code:
+//     cfg 0  128x64  tile, 4 warps (2x2), 3-stage ring, TWO CTAs per SM: while one CTA sits at its
+//            slab barrier, issues its cp.async or runs its epilogue, the other keeps the DMMA pipe fed.
+//     cfg 1  128x128 tile, 8 warps (2x4), 4-stage ring, one CTA per SM.
+//   A (k contiguous) and B (n contiguous) k-slabs of 16 are staged global->shared with 16-byte
+//   cp.async (LDGSTS), one __syncthreads per slab; the copies for slab kt+S-1 are issued AFTER the
+//   first quarter of slab kt's DMMAs so the tensor pipe never waits on address arithmetic.  Source
+//   pointers/predicates are hoisted: full slabs advance by a constant stride, only the last
+//   (ragged) slab re-evaluates k bounds.
+//   Shared rows are padded by 4 doubles so the 8-byte fragment loads of a half-warp hit 32 distinct
+//   banks for both operands (ncu: 0 bank conflicts):
+//     A frag  As[row=g][k=t]   : word = row*40 + 2k        -> bank 8g+2t (+0/1)
+//     B frag  Bs[k=t][col=g]   : word = k*(2*BN+8) + 2col  -> bank 8t+2g (+0/1)
+//   Tiles are rasterised in bands of 16 tile-rows so co-resident CTAs share A and B slabs in L2.
+//   beta == 0 never reads C (mat_mul.rs:52-55 hands over uninitialised memory); beta != 0 loads C in
+//   batches of 8 independent 16-byte loads before the FMAs (rank-k updates are epilogue-heavy).
 #include "common.cuh"
 
 namespace rla {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 4, THREADS = 256;
+constexpr int BK = 16;
 constexpr int LDAS = BK + 4;             // padded A row (doubles)
-constexpr int LDBS = BN + 4;             // padded B row (doubles)
-constexpr int A_STAGE = BM * LDAS;       // doubles per stage
-constexpr int B_STAGE = BK * LDBS;
-constexpr size_t SMEM_BYTES = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(double);
 constexpr int BAND = 16;                 // tile-rows per raster band
 
-template <bool ALIGNED>
-__device__ __forceinline__ void load_slab(double *As, double *Bs, const double *__restrict__ A,
-                                          size_t lda, const double *__restrict__ B, size_t ldb,
-                                          int M, int N, int K, int m0, int n0, int k0, int tid) {
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+struct Cfg {
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int THREADS = WM * WN * 32;
+    static constexpr int LDBS = BN + 4;
+    static constexpr int A_STAGE = BM * LDAS;
+    static constexpr int B_STAGE = BK * LDBS;
+    static constexpr size_t SMEM = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(double);
+    static constexpr int A_CHUNKS = BM * (BK / 2) / THREADS;       // 16-byte chunks per thread per slab
+    static constexpr int B_CHUNKS = BK * (BN / 2) / THREADS;
+    static_assert(BM == WM * 64 && BN == WN * 32, "warp tile is 64x32");
+    static_assert(A_CHUNKS * THREADS == BM * (BK / 2) && B_CHUNKS * THREADS == BK * (BN / 2), "chunking");
+};
+using CfgSmall = Cfg<128, 64, 2, 2, 3, 2>;
+using CfgLarge = Cfg<128, 128, 2, 4, 4, 1>;
+
+// Per-thread copy plan for the aligned (16-byte) path.  Thread `tid` always copies chunk column
+// `tid % chunks_per_row` of rows `tid / chunks_per_row + i * rows_per_pass`: one base pointer per
+// operand plus a constant row stride, so the per-slab address arithmetic is a handful of IMADs.
+template <class C>
+struct CopyPlan {
+    static constexpr int ACH = BK / 2, A_ROWS = C::THREADS / ACH;        // A: chunks per row, rows per pass
+    static constexpr int BCH = C::BN / 2, B_ROWS = C::THREADS / BCH;     // B
+    static_assert(A_ROWS * C::A_CHUNKS == C::BM && B_ROWS * C::B_CHUNKS == BK, "copy plan");
+    const double *a_src;     // A + (m0 + row0)*lda + 2*ch
+    const double *b_src;     // B + row0*ldb + n0 + 2*ch
+    size_t a_step, b_step;   // elements between passes (A_ROWS*lda, B_ROWS*ldb)
+    uint32_t a_dst, b_dst;   // shared byte offsets inside a stage
+    uint32_t a_valid;        // bit i: row of pass i is inside M
+    int a_k, b_k, b_bytes;   // k offset inside a slab (A chunk / B row of pass 0); B bytes (16/8/0)
+};
+
+template <class C, bool ALIGNED>
+__device__ __forceinline__ void issue_slab(const CopyPlan<C> &p, uint32_t as_base, uint32_t bs_base, int k0, int K,
+                                           size_t ldb, bool full, const double *A, const double *B, size_t lda,
+                                           int M, int N, int m0, int n0, int tid) {
     if (ALIGNED) {
-        // A: 128 rows x 8 chunks of 2 doubles
-        const int ca = tid & 7, ra = tid >> 3;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = ra + 32 * i;
-            const int gk = k0 + 2 * ca;
-            int bytes = 0;
-            const double *src = A;
-            if (m0 + row < M && gk < K) {
-                bytes = (K - gk >= 2) ? 16 : 8;
-                src = A + size_t(m0 + row) * lda + gk;
-            }
-            cp_async16(smem_u32(As + row * LDAS + 2 * ca), src, bytes);
+        using P = CopyPlan<C>;
+        int abytes = 16;
+        if (!full) {
+            const int rem = K - (k0 + p.a_k);
+            abytes = rem >= 2 ? 16 : (rem == 1 ? 8 : 0);
         }
-        // B: 16 rows x 64 chunks
-        const int cb = tid & 63, rb = tid >> 6;
+        const double *asrc = p.a_src + k0;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int row = rb + 4 * i;
-            const int gn = n0 + 2 * cb;
-            int bytes = 0;
-            const double *src = B;
-            if (k0 + row < K && gn < N) {
-                bytes = (N - gn >= 2) ? 16 : 8;
-                src = B + size_t(k0 + row) * ldb + gn;
-            }
-            cp_async16(smem_u32(Bs + row * LDBS + 2 * cb), src, bytes);
+        for (int i = 0; i < C::A_CHUNKS; ++i) {
+            const int bytes = ((p.a_valid >> i) & 1u) ? abytes : 0;
+            cp_async16(as_base + p.a_dst + i * (P::A_ROWS * LDAS * 8), bytes ? asrc + i * p.a_step : A, bytes);
+        }
+        const double *bsrc = p.b_src + size_t(k0) * ldb;
+#pragma unroll
+        for (int i = 0; i < C::B_CHUNKS; ++i) {
+            int bytes = p.b_bytes;
+            if (!full && k0 + p.b_k + i * P::B_ROWS >= K) bytes = 0;
+            cp_async16(bs_base + p.b_dst + i * (P::B_ROWS * C::LDBS * 8), bytes ? bsrc + i * p.b_step : B, bytes);
         }
     } else {
-        // 8-byte path for odd leading dimensions / unaligned bases
-        const int ca = tid & 15, ra = tid >> 4;
+        // 8-byte path for odd leading dimensions / unaligned bases (bounds evaluated per element)
+        constexpr int AE = C::BM * BK / C::THREADS, BE = BK * C::BN / C::THREADS;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = ra + 16 * i;
-            const int gk = k0 + ca;
-            const bool ok = (m0 + row < M) && (gk < K);
-            const double *src = ok ? A + size_t(m0 + row) * lda + gk : A;
-            cp_async8(smem_u32(As + row * LDAS + ca), src, ok ? 8 : 0);
+        for (int i = 0; i < AE; ++i) {
+            const int e = tid + i * C::THREADS;
+            const int row = e / BK, kk = e % BK;
+            const bool ok = (m0 + row < M) && (k0 + kk < K);
+            cp_async8(as_base + (row * LDAS + kk) * 8, ok ? A + size_t(m0 + row) * lda + k0 + kk : A, ok ? 8 : 0);
         }
-        const int cb = tid & 127, rb = tid >> 7;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = rb + 2 * i;
-            const int gn = n0 + cb;
-            const bool ok = (k0 + row < K) && (gn < N);
-            const double *src = ok ? B + size_t(k0 + row) * ldb + gn : B;
-            cp_async8(smem_u32(Bs + row * LDBS + cb), src, ok ? 8 : 0);
+        for (int i = 0; i < BE; ++i) {
+            const int e = tid + i * C::THREADS;
+            const int row = e / C::BN, cc = e % C::BN;
+            const bool ok = (k0 + row < K) && (n0 + cc < N);
+            cp_async8(bs_base + (row * C::LDBS + cc) * 8, ok ? B + size_t(k0 + row) * ldb + n0 + cc : B, ok ? 8 : 0);
         }
     }
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(THREADS, 1)
+template <class C>
+__device__ __forceinline__ void mma_k4(double (&acc)[8][4][2], const double *ap, const double *bp, int kk) {
+    double af[8], bf[4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) af[i] = ap[i * 8 * LDAS + kk];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) bf[j] = bp[kk * C::LDBS + j * 8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+}
+
+template <class C, bool ALIGNED>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
 dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, size_t lda,
-                  const double *__restrict__ B, size_t ldb, double beta, double *__restrict__ C,
+                  const double *__restrict__ B, size_t ldb, double beta, double *__restrict__ Cmat,
                   size_t ldc, int tiles_m, int tiles_n) {
     extern __shared__ __align__(16) double smem[];
     double *As = smem;
-    double *Bs = smem + STAGES * A_STAGE;
+    double *Bs = smem + C::STAGES * C::A_STAGE;
 
     // band-rasterised tile order
     const int bid = blockIdx.x;
@@ -101,12 +137,33 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
     const int band_rows = min(BAND, tiles_m - band * BAND);
     const int tm = band * BAND + rem % band_rows;
     const int tn = rem / band_rows;
-    const int m0 = tm * BM, n0 = tn * BN;
+    const int m0 = tm * C::BM, n0 = tn * C::BN;
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
-    const int wm = warp & 1, wn = warp >> 1;
+    const int wm = warp % C::WM, wn = warp / C::WM;
+
+    CopyPlan<C> plan;
+    if (ALIGNED) {
+        using P = CopyPlan<C>;
+        const int arow = tid / P::ACH, ach = tid % P::ACH;
+        plan.a_k = 2 * ach;
+        plan.a_dst = (arow * LDAS + 2 * ach) * 8;
+        plan.a_step = size_t(P::A_ROWS) * lda;
+        plan.a_valid = 0;
+#pragma unroll
+        for (int i = 0; i < C::A_CHUNKS; ++i)
+            if (m0 + arow + i * P::A_ROWS < M) plan.a_valid |= 1u << i;
+        plan.a_src = A + size_t(m0 + arow) * lda + 2 * ach;
+        const int brow = tid / P::BCH, bch = tid % P::BCH;
+        plan.b_k = brow;
+        plan.b_dst = (brow * C::LDBS + 2 * bch) * 8;
+        plan.b_step = size_t(P::B_ROWS) * ldb;
+        const int gn = n0 + 2 * bch;
+        plan.b_bytes = gn + 1 < N ? 16 : (gn < N ? 8 : 0);
+        plan.b_src = B + size_t(brow) * ldb + (gn < N ? gn : 0);
+    }
 
     double acc[8][4][2];
 #pragma unroll
@@ -115,52 +172,81 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int KT = (K + BK - 1) / BK;
+    const int KT_FULL = K / BK;                  // slabs needing no k-bound checks
+    const uint32_t as_u32 = smem_u32(As), bs_u32 = smem_u32(Bs);
 
 #pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) load_slab<ALIGNED>(As + s * A_STAGE, Bs + s * B_STAGE, A, lda, B, ldb, M, N, K, m0, n0, s * BK, tid);
+    for (int s = 0; s < C::STAGES - 1; ++s) {
+        if (s < KT)
+            issue_slab<C, ALIGNED>(plan, as_u32 + s * C::A_STAGE * 8, bs_u32 + s * C::B_STAGE * 8, s * BK, K, ldb,
+                                   s < KT_FULL, A, B, lda, M, N, m0, n0, tid);
         cp_async_commit();
     }
 
     const double *a_frag_base = As + (wm * 64 + g) * LDAS + t;
-    const double *b_frag_base = Bs + t * LDBS + wn * 32 + g;
+    const double *b_frag_base = Bs + t * C::LDBS + wn * 32 + g;
 
+    int stage = 0;
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
+        cp_async_wait<C::STAGES - 2>();
         __syncthreads();
-        {
-            const int nk = kt + STAGES - 1;
+        const double *ap = a_frag_base + stage * C::A_STAGE;
+        const double *bp = b_frag_base + stage * C::B_STAGE;
+        mma_k4<C>(acc, ap, bp, 0);               // feed the tensor pipe first ...
+        {                                        // ... then queue the copies for slab kt+STAGES-1
+            const int nk = kt + C::STAGES - 1;
             if (nk < KT) {
-                const int s = nk % STAGES;
-                load_slab<ALIGNED>(As + s * A_STAGE, Bs + s * B_STAGE, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
+                int ns = stage + C::STAGES - 1;
+                if (ns >= C::STAGES) ns -= C::STAGES;
+                issue_slab<C, ALIGNED>(plan, as_u32 + ns * C::A_STAGE * 8, bs_u32 + ns * C::B_STAGE * 8, nk * BK, K, ldb,
+                                       nk < KT_FULL, A, B, lda, M, N, m0, n0, tid);
             }
             cp_async_commit();
         }
-        const int s = kt % STAGES;
-        const double *ap = a_frag_base + s * A_STAGE;
-        const double *bp = b_frag_base + s * B_STAGE;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            double af[8], bf[4];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) af[i] = ap[i * 8 * LDAS + kk];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) bf[j] = bp[kk * LDBS + j * 8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-#pragma unroll
-                for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
-        }
+        mma_k4<C>(acc, ap, bp, 4);
+        mma_k4<C>(acc, ap, bp, 8);
+        mma_k4<C>(acc, ap, bp, 12);
+        if (++stage == C::STAGES) stage = 0;
     }
     cp_async_wait<0>();
 
     // epilogue: thread owns C[row g][cols 2t,2t+1] of each 8x8 fragment
-    const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+    const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cmat) & 15) == 0);
+    const bool interior = vec_ok && (m0 + C::BM <= M) && (n0 + C::BN <= N);
+    double *cbase = Cmat + size_t(m0 + wm * 64 + g) * ldc + n0 + wn * 32 + 2 * t;
+    if (interior) {
+        if (beta == 0.0) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<double2 *>(cbase + size_t(i * 8) * ldc + j * 8) =
+                        make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
+        } else {
+#pragma unroll
+            for (int ib = 0; ib < 8; ib += 2) {
+                double2 old[2][4];
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        old[i][j] = *reinterpret_cast<const double2 *>(cbase + size_t((ib + i) * 8) * ldc + j * 8);
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<double2 *>(cbase + size_t((ib + i) * 8) * ldc + j * 8) =
+                            make_double2(alpha * acc[ib + i][j][0] + beta * old[i][j].x,
+                                         alpha * acc[ib + i][j][1] + beta * old[i][j].y);
+            }
+        }
+        return;
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         const int row = m0 + wm * 64 + i * 8 + g;
         if (row >= M) continue;
-        double *crow = C + size_t(row) * ldc;
+        double *crow = Cmat + size_t(row) * ldc;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int col = n0 + wn * 32 + j * 8 + 2 * t;
@@ -186,7 +272,7 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
     }
 }
 
-// k == 0 (or alpha == 0 shortcut not used): C <- beta*C, zero-fill when beta == 0 without reading C.
+// k == 0: C <- beta*C, zero-fill when beta == 0 without reading C.
 template <typename T>
 __global__ void scale_c_kernel(size_t M, size_t N, T beta, T *C, size_t ldc) {
     const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -196,7 +282,27 @@ __global__ void scale_c_kernel(size_t M, size_t N, T beta, T *C, size_t ldc) {
     *p = (beta == T(0)) ? T(0) : (*p) * beta;
 }
 
+template <class C, bool ALIGNED>
+int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
+               double beta, double *c, size_t ldc, cudaStream_t st) {
+    static bool attr_set = false;
+    const int tiles_m = int((m + C::BM - 1) / C::BM), tiles_n = int((n + C::BN - 1) / C::BN);
+    const size_t tiles = size_t(tiles_m) * tiles_n;
+    if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
+    if (!attr_set) {
+        RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+        RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_set = true;
+    }
+    dgemm_dmma_kernel<C, ALIGNED><<<unsigned(tiles), C::THREADS, C::SMEM, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
+                                                                                beta, c, ldc, tiles_m, tiles_n);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
 }  // namespace
+
+int g_dgemm_cfg = 0;   // 0 = 128x64 (2 CTAs/SM), 1 = 128x128 (1 CTA/SM); rla_set_tuning("dgemm_cfg", v)
 
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st) {
@@ -216,31 +322,15 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     if (m == 0 || n == 0) return RLA_OK;
     if (k == 0) return scale_c_launch<double>(m, n, beta, c, ldc, st);
     if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
-
-    static bool attr_set[2] = {false, false};
     const bool aligned = ((lda & 1) == 0) && ((ldb & 1) == 0) &&
                          ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
-    const int tiles_m = int((m + BM - 1) / BM), tiles_n = int((n + BN - 1) / BN);
-    const size_t tiles = size_t(tiles_m) * tiles_n;
-    if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
-    if (aligned) {
-        if (!attr_set[1]) {
-            RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-            attr_set[1] = true;
-        }
-        dgemm_dmma_kernel<true><<<unsigned(tiles), THREADS, SMEM_BYTES, st>>>(
-            int(m), int(n), int(k), alpha, a, lda, b, ldb, beta, c, ldc, tiles_m, tiles_n);
-    } else {
-        if (!attr_set[0]) {
-            RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-            attr_set[0] = true;
-        }
-        dgemm_dmma_kernel<false><<<unsigned(tiles), THREADS, SMEM_BYTES, st>>>(
-            int(m), int(n), int(k), alpha, a, lda, b, ldb, beta, c, ldc, tiles_m, tiles_n);
+    if (g_dgemm_cfg == 1) {
+        return aligned ? launch_cfg<CfgLarge, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
+                       : launch_cfg<CfgLarge, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     }
-    RLA_LAUNCHED();
-    return RLA_OK;
+    return aligned ? launch_cfg<CfgSmall, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
+                   : launch_cfg<CfgSmall, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
 }  // namespace rla

@@ -55,14 +55,50 @@ __device__ __forceinline__ bool cand_better(T va, int ia, T vb, int ib) {
 }
 
 // -------------------------------------------------------------------------------------------
-// Panel factorisation of A[J:n, J:J+jb].  Grid = G CTAs (cooperative), CTA b owns rows
-// [J + b*R, J + (b+1)*R).  scratch: cand_abs[2][G], cand_idx[2][G], rowbuf[2][G][PW], diagbuf[2][PW].
+// Panel factorisation of A[J:n, J:J+jb].  Cooperative grid of G "row" CTAs (+1 optional "swapper"
+// CTA).  Row CTA b keeps rows [J + b*R, J + (b+1)*R) of the panel in shared memory.
+//
+// One grid-wide exchange per column, with NO separate barrier object: every row CTA publishes a
+// 16-byte packet {|max| (f64), row index, tag} -- preceded by the candidate row's contents -- and
+// then polls the G packets until all carry the tag of this column; the data arrival IS the barrier.
+// Tags are unique per (panel launch, column), buffers alternate by column parity: a CTA can only be
+// one column ahead of the slowest one, because it needs everybody's packet to advance.
+//
+// The swapper CTA never publishes, so nobody waits for it: it follows the pivot log written by CTA 0
+// and applies each interchange to the columns of the enclosing outer block that lie outside this
+// panel (what used to be a separate, latency-bound "inner laswp" launch).
 // -------------------------------------------------------------------------------------------
+struct __align__(16) Packet {
+    double absval;
+    int idx;
+    unsigned tag;
+};
+__device__ __forceinline__ void packet_store(Packet *p, double a, int idx, unsigned tag) {
+    const unsigned long long lo = (unsigned long long)__double_as_longlong(a);
+    const unsigned long long hi = (unsigned long long)(unsigned)idx | ((unsigned long long)tag << 32);
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
+}
+__device__ __forceinline__ void packet_load(const Packet *p, double &a, int &idx, unsigned &tag) {
+    unsigned long long lo, hi;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+    a = __longlong_as_double((long long)lo);
+    idx = int(unsigned(hi & 0xffffffffull));
+    tag = unsigned(hi >> 32);
+}
+
+struct PanelScratch {
+    Packet *packets;                 // [2][GMAX]
+    void *rowbuf;                    // [2][GMAX][PW] of T
+    void *diagbuf;                   // [2][PW] of T
+    unsigned long long *piv_log;     // [PW]  (tag << 32 | pivot row) written by CTA 0
+};
+constexpr int GMAX = 256;
+
 template <typename T>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
-lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32_t *__restrict__ ipiv,
-                int32_t *__restrict__ info, T *cand_abs, int *cand_idx, T *rowbuf, T *diagbuf,
-                unsigned *bar, unsigned bar_base) {
+lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G, int32_t *__restrict__ ipiv,
+                int32_t *__restrict__ info, PanelScratch sc, unsigned tag_base, int sw_c0a, int sw_c1a, int sw_c0b,
+                int sw_c1b) {
     if (*info != 0) return;   // an earlier panel hit a tiny pivot: written by a previous kernel => uniform
     extern __shared__ __align__(16) unsigned char panel_smem[];
     T *s = reinterpret_cast<T *>(panel_smem);
@@ -72,8 +108,39 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32
     __shared__ T sh_abs;
     __shared__ int sh_idx, sh_win;
 
-    const int G = gridDim.x, b = blockIdx.x, tid = threadIdx.x;
+    const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    T *rowbuf = static_cast<T *>(sc.rowbuf);
+    T *diagbuf = static_cast<T *>(sc.diagbuf);
+
+    if (b >= G) {
+        // ---------------- swapper CTA ----------------
+        const int na = sw_c1a - sw_c0a, ncols = na + (sw_c1b - sw_c0b);
+        const int col = (tid < na) ? sw_c0a + tid : sw_c0b + (tid - na);
+        for (int c = 0; c < jb; ++c) {
+            if (tid == 0) {
+                const unsigned want = tag_base + unsigned(c) + 1u;
+                unsigned long long v;
+                do {
+                    v = *((volatile unsigned long long *)(sc.piv_log + c));
+                } while (unsigned(v >> 32) != want);
+                sh_idx = int(unsigned(v & 0xffffffffull));
+            }
+            __syncthreads();
+            const int p = sh_idx;
+            __syncthreads();
+            if (p < 0) return;                       // singular: CTA 0 logged -1
+            const int d = J + c;
+            if (p != d && tid < ncols) {
+                T *rd = A + size_t(d) * ld + col, *rp = A + size_t(p) * ld + col;
+                const T vd = *rd, vp = *rp;
+                *rd = vp;
+                *rp = vd;
+            }
+        }
+        return;
+    }
+
     const int r0 = J + b * R;
     const int r1 = min(n, r0 + R);
     const int nrows = max(0, r1 - r0);
@@ -87,6 +154,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32
     for (int c = 0; c < jb; ++c) {
         const int d = J + c;                       // global diagonal row of this column
         const int par = c & 1;
+        const unsigned tag = tag_base + unsigned(c) + 1u;
         const int lo = max(0, d - r0);             // first local row still active
         const bool owns_d = (d >= r0 && d < r1);
 
@@ -123,38 +191,41 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32
                 }
                 sh_abs = best;
                 sh_idx = bidx;
-                cand_abs[par * G + b] = best;
-                cand_idx[par * G + b] = bidx;
             }
         }
         __syncthreads();
-        // ---- post the candidate row (and the diagonal row) so the winner's contents are global ----
+        // ---- publish: candidate row (and the diagonal row) first, then the tagged packet ----
         {
             const int li = sh_idx;
-            if (li != INT_MAX && tid < jb) rowbuf[size_t(par * G + b) * PW + tid] = s[(li - r0) * PLDS + tid];
-            if (owns_d && tid >= 64 && tid < 64 + jb) diagbuf[par * PW + (tid - 64)] = s[(d - r0) * PLDS + (tid - 64)];
+            if (li != INT_MAX && tid < jb) {
+                rowbuf[size_t(par * GMAX + b) * PW + tid] = s[(li - r0) * PLDS + tid];
+                __threadfence();
+            }
+            if (owns_d && tid >= 64 && tid < 64 + jb) {
+                diagbuf[par * PW + (tid - 64)] = s[(d - r0) * PLDS + (tid - 64)];
+                __threadfence();
+            }
         }
-        __threadfence();
         __syncthreads();
-        // ---- grid-wide barrier (monotonic counter) ----
         if (tid == 0) {
             __threadfence();
-            atomicAdd(bar, 1u);
-            const unsigned target = bar_base + unsigned(c + 1) * unsigned(G);
-            while (int(*((volatile unsigned *)bar) - target) < 0) {
-            }
-            __threadfence();
+            packet_store(sc.packets + par * GMAX + b, double(sh_abs), sh_idx, tag);
         }
-        __syncthreads();
-        // ---- global reduce over the G posted candidates (every CTA, redundantly) ----
+        // ---- gather: poll all G packets of this column, reduce (every CTA, redundantly) ----
         if (warp == 0) {
             T gv = T(-1);
             int gi = INT_MAX, gw = 0;
             for (int q = lane; q < G; q += 32) {
-                const T v = __ldcg(cand_abs + par * G + q);
-                const int i = __ldcg(cand_idx + par * G + q);
+                double a;
+                int i;
+                unsigned tg;
+                do {
+                    packet_load(sc.packets + par * GMAX + q, a, i, tg);
+                } while (tg != tag);
+                const T v = T(a);
                 if (cand_better(v, i, gv, gi)) { gv = v; gi = i; gw = q; }
             }
+            __threadfence();
 #pragma unroll
             for (int off = 16; off > 0; off >>= 1) {
                 const T ov = __shfl_down_sync(0xffffffffu, gv, off);
@@ -168,11 +239,17 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32
         const T pabs = sh_abs;
         const int prow_idx = sh_idx, win = sh_win;
         if (pabs < Eps<T>::v()) {                  // lu.rs:179-183 (NaN: comparison false, continues)
-            if (b == 0 && tid == 0) *info = d + 1;
+            if (b == 0 && tid == 0) {
+                *info = d + 1;
+                sc.piv_log[c] = ((unsigned long long)tag << 32) | 0xffffffffull;   // tell the swapper to stop
+            }
             return;                                // uniform across the grid
         }
-        if (tid < jb) prow_s[tid] = __ldcg(rowbuf + size_t(par * G + win) * PW + tid);
-        if (b == 0 && tid == 0) ipiv[d] = prow_idx;
+        if (tid < jb) prow_s[tid] = __ldcg(rowbuf + size_t(par * GMAX + win) * PW + tid);
+        if (b == 0 && tid == 0) {
+            ipiv[d] = prow_idx;
+            sc.piv_log[c] = ((unsigned long long)tag << 32) | (unsigned long long)(unsigned)prow_idx;
+        }
         __syncthreads();
         if (prow_idx != d) {                       // swap rows d <-> prow_idx inside the panel
             if (owns_d && tid < jb) s[(d - r0) * PLDS + tid] = prow_s[tid];
@@ -202,133 +279,162 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32
 }
 
 // -------------------------------------------------------------------------------------------
-// laswp: apply interchanges (J+k <-> ipiv[J+k]), k = 0..jb-1, to columns [c0a,c1a) U [c0b,c1b) as one
-// gather.  "Touched" rows: index i < jb -> row J+i; index jb+f -> far row fr[f].  origin[i] = touched
-// index whose OLD contents end up in touched row i.  If rowid != nullptr CTA 0 also permutes it.
+// laswp for a whole outer block: interchanges (J+k <-> ipiv[J+k]), k = 0..jb-1 (jb <= 256), applied
+// to the columns left and right of the block as ONE gather instead of jb dependent swaps.
+//   plan kernel (one warp): simulate the interchanges on indices.  "Touched" rows: index i < jb ->
+//     row J+i; index jb+f -> far row fr[f].  origin[i] = touched index whose OLD contents end up in
+//     touched row i.  Also permutes the row-origin vector from which `perm` is produced.
+//   apply kernel: each CTA owns 32 columns; reads every source row segment into shared memory
+//     (8 independent loads in flight per lane), then writes the destinations.
 // -------------------------------------------------------------------------------------------
-constexpr int LASWP_THREADS = 256;
 constexpr int LASWP_MAXJB = OUTER_W;
+struct LaswpPlan {
+    int nt;
+    int rows[2 * LASWP_MAXJB];
+    int origin[2 * LASWP_MAXJB];
+};
 
-template <typename T>
-__global__ void __launch_bounds__(LASWP_THREADS)
-laswp_kernel(T *__restrict__ A, size_t ld, int J, int jb, const int32_t *__restrict__ ipiv,
-             const int32_t *__restrict__ info, int c0a, int c1a, int c0b, int c1b, int CW,
-             int32_t *__restrict__ rowid) {
+__global__ void __launch_bounds__(32)
+laswp_plan_kernel(int J, int jb, const int32_t *__restrict__ ipiv, const int32_t *__restrict__ info,
+                  LaswpPlan *__restrict__ plan, int32_t *__restrict__ rowid) {
     if (*info != 0) return;
-    extern __shared__ __align__(16) unsigned char laswp_smem[];
-    T *tile = reinterpret_cast<T *>(laswp_smem);
     __shared__ int od[LASWP_MAXJB];       // origin of dense touched rows
     __shared__ int fr[LASWP_MAXJB];       // far row numbers
     __shared__ int of[LASWP_MAXJB];       // origin of far touched rows
     __shared__ int piv_s[LASWP_MAXJB];
-    __shared__ int nf_s;
-
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int i = tid; i < jb; i += LASWP_THREADS) {
+    __shared__ int ids[2 * LASWP_MAXJB];
+    const int lane = threadIdx.x;
+    for (int i = lane; i < jb; i += 32) {
         od[i] = i;
         piv_s[i] = ipiv[J + i];
     }
-    __syncthreads();
-    if (warp == 0) {
-        int nf = 0;
-        for (int k = 0; k < jb; ++k) {
-            const int bq = piv_s[k];
-            if (bq == J + k) continue;
-            if (bq < J + jb) {
-                if (lane == 0) { const int t = od[k]; od[k] = od[bq - J]; od[bq - J] = t; }
-            } else {
-                int f = -1;
-                for (int base = 0; base < nf; base += 32) {
-                    const int q = base + lane;
-                    const unsigned hit = __ballot_sync(0xffffffffu, q < nf && fr[q] == bq);
-                    if (hit) { f = base + __ffs(hit) - 1; break; }
-                }
-                if (f < 0) {
-                    f = nf++;
-                    if (lane == 0) { fr[f] = bq; of[f] = jb + f; }
-                }
-                __syncwarp();
-                if (lane == 0) { const int t = od[k]; od[k] = of[f]; of[f] = t; }
+    __syncwarp();
+    int nf = 0;
+    for (int k = 0; k < jb; ++k) {
+        const int bq = piv_s[k];
+        if (bq == J + k) continue;
+        if (bq < J + jb) {
+            if (lane == 0) { const int t = od[k]; od[k] = od[bq - J]; od[bq - J] = t; }
+        } else {
+            int f = -1;
+            for (int base = 0; base < nf; base += 32) {
+                const int q = base + lane;
+                const unsigned hit = __ballot_sync(0xffffffffu, q < nf && fr[q] == bq);
+                if (hit) { f = base + __ffs(hit) - 1; break; }
+            }
+            if (f < 0) {
+                f = nf++;
+                if (lane == 0) { fr[f] = bq; of[f] = jb + f; }
             }
             __syncwarp();
+            if (lane == 0) { const int t = od[k]; od[k] = of[f]; of[f] = t; }
         }
-        if (lane == 0) nf_s = nf;
+        __syncwarp();
     }
-    __syncthreads();
-    const int nf = nf_s;
     const int nt = jb + nf;
-
-    // the row-origin vector rides along as one extra "column"
-    if (rowid != nullptr && blockIdx.x == 0) {
-        int *itile = reinterpret_cast<int *>(tile);
-        for (int i = tid; i < nt; i += LASWP_THREADS) itile[i] = rowid[(i < jb) ? J + i : fr[i - jb]];
-        __syncthreads();
-        for (int i = tid; i < nt; i += LASWP_THREADS) {
-            const int o = (i < jb) ? od[i] : of[i - jb];
-            if (o != i) rowid[(i < jb) ? J + i : fr[i - jb]] = itile[o];
-        }
-        __syncthreads();
+    if (lane == 0) plan->nt = nt;
+    for (int i = lane; i < nt; i += 32) {
+        plan->rows[i] = (i < jb) ? J + i : fr[i - jb];
+        plan->origin[i] = (i < jb) ? od[i] : of[i - jb];
     }
+    // the row-origin vector rides along
+    for (int i = lane; i < nt; i += 32) ids[i] = rowid[(i < jb) ? J + i : fr[i - jb]];
+    __syncwarp();
+    for (int i = lane; i < nt; i += 32) {
+        const int o = (i < jb) ? od[i] : of[i - jb];
+        if (o != i) rowid[(i < jb) ? J + i : fr[i - jb]] = ids[o];
+    }
+}
 
+constexpr int LASWP_THREADS = 512;
+constexpr int LASWP_CW = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(LASWP_THREADS)
+laswp_apply_kernel(T *__restrict__ A, size_t ld, const LaswpPlan *__restrict__ plan, const int32_t *__restrict__ info,
+                   int c0a, int c1a, int c0b, int c1b) {
+    if (*info != 0) return;
+    extern __shared__ __align__(16) unsigned char laswp_smem[];
+    T *tile = reinterpret_cast<T *>(laswp_smem);                 // [nt][LASWP_CW]
+    __shared__ int rows_s[2 * LASWP_MAXJB];
+    __shared__ int org_s[2 * LASWP_MAXJB];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nt = plan->nt;
+    for (int i = tid; i < nt; i += LASWP_THREADS) {
+        rows_s[i] = plan->rows[i];
+        org_s[i] = plan->origin[i];
+    }
+    __syncthreads();
     const int na = c1a - c0a, ncols = na + (c1b - c0b);
-    const int chunk0 = blockIdx.x * CW;
-    if (chunk0 >= ncols) return;
-    const int cw = min(CW, ncols - chunk0);
-    // gather all touched rows of this column chunk
-    for (int i = warp; i < nt; i += LASWP_THREADS / 32) {
-        const int row = (i < jb) ? J + i : fr[i - jb];
-        const T *src = A + size_t(row) * ld;
-        for (int cc = lane; cc < cw; cc += 32) {
-            const int q = chunk0 + cc;
-            const int col = (q < na) ? c0a + q : c0b + (q - na);
-            tile[i * CW + cc] = src[col];
+    const int q = blockIdx.x * LASWP_CW + lane;
+    const bool ok = q < ncols;
+    const int col = ok ? ((q < na) ? c0a + q : c0b + (q - na)) : 0;
+    constexpr int NW = LASWP_THREADS / 32, UNR = 8;
+    // read phase: tile[i] <- old contents of the row that ends up in touched row i
+    for (int i0 = warp; i0 < nt; i0 += NW * UNR) {
+        T v[UNR];
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * NW;
+            v[u] = T(0);
+            if (i < nt && ok && org_s[i] != i) v[u] = A[size_t(rows_s[org_s[i]]) * ld + col];
+        }
+#pragma unroll
+        for (int u = 0; u < UNR; ++u) {
+            const int i = i0 + u * NW;
+            if (i < nt) tile[i * LASWP_CW + lane] = v[u];
         }
     }
     __syncthreads();
-    for (int i = warp; i < nt; i += LASWP_THREADS / 32) {
-        const int o = (i < jb) ? od[i] : of[i - jb];
-        if (o == i) continue;
-        const int row = (i < jb) ? J + i : fr[i - jb];
-        T *dst = A + size_t(row) * ld;
-        for (int cc = lane; cc < cw; cc += 32) {
-            const int q = chunk0 + cc;
-            const int col = (q < na) ? c0a + q : c0b + (q - na);
-            dst[col] = tile[o * CW + cc];
-        }
+    for (int i = warp; i < nt; i += NW) {
+        if (ok && org_s[i] != i) A[size_t(rows_s[i]) * ld + col] = tile[i * LASWP_CW + lane];
     }
 }
 
 // -------------------------------------------------------------------------------------------
 // trsm: B <- L^-1 B, L = unit lower jb x jb (jb <= 64) at A[j:j+jb, j:j+jb], B = A[j:j+jb, c0:c1).
-// Thread per column, the column lives in registers; L is broadcast from shared memory.
+// Four threads per column (rows interleaved mod 4, 16 values each in registers); x_k is broadcast
+// inside the 4-thread group with a shuffle, L is read from shared memory.
 // -------------------------------------------------------------------------------------------
 constexpr int TRSM_THREADS = 128;
+constexpr int TRSM_COLS = TRSM_THREADS / 4;
 
 template <typename T>
 __global__ void __launch_bounds__(TRSM_THREADS)
 trsm_unit_lower_kernel(T *__restrict__ A, size_t ld, int j, int jb, int c0, int c1,
                        const int32_t *__restrict__ info) {
     if (*info != 0) return;
-    __shared__ T Ls[PW * PW];
+    __shared__ T Ls[PW * (PW + 1)];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < PW * PW; idx += TRSM_THREADS) {
         const int r = idx / PW, c = idx - r * PW;
-        Ls[idx] = (r < jb && c < r) ? A[size_t(j + r) * ld + j + c] : T(0);
+        Ls[r * (PW + 1) + c] = (r < jb && c < r) ? A[size_t(j + r) * ld + j + c] : T(0);
     }
     __syncthreads();
-    const int col = c0 + blockIdx.x * TRSM_THREADS + tid;
-    if (col >= c1) return;
-    T x[PW];
+    const int lane = tid & 31;
+    const int r = lane & 3;                                   // row residue owned by this thread
+    const int col = c0 + blockIdx.x * TRSM_COLS + (tid >> 5) * 8 + (lane >> 2);
+    const bool ok = col < c1;
+    T x[PW / 4];
 #pragma unroll
-    for (int i = 0; i < PW; ++i) x[i] = (i < jb) ? A[size_t(j + i) * ld + col] : T(0);
+    for (int ii = 0; ii < PW / 4; ++ii) {
+        const int i = 4 * ii + r;
+        x[ii] = (ok && i < jb) ? A[size_t(j + i) * ld + col] : T(0);
+    }
+    const T *Lr = Ls + r * (PW + 1);
 #pragma unroll
     for (int k = 0; k < PW - 1; ++k) {
+        const T xk = __shfl_sync(0xffffffffu, x[k >> 2], (lane & ~3) | (k & 3));
 #pragma unroll
-        for (int i = k + 1; i < PW; ++i) x[i] -= Ls[i * PW + k] * x[k];
+        for (int ii = (k >> 2); ii < PW / 4; ++ii) {
+            if (ii > (k >> 2) || r > (k & 3)) x[ii] -= Lr[(4 * ii) * (PW + 1) + k] * xk;
+        }
     }
 #pragma unroll
-    for (int i = 1; i < PW; ++i)
-        if (i < jb) A[size_t(j + i) * ld + col] = x[i];
+    for (int ii = 0; ii < PW / 4; ++ii) {
+        const int i = 4 * ii + r;
+        if (ok && i >= 1 && i < jb) A[size_t(j + i) * ld + col] = x[ii];
+    }
 }
 
 __global__ void iota_kernel(int32_t *p, int n) {
@@ -361,21 +467,19 @@ int g_num_sms = 0;
 
 template <typename T>
 int launch_laswp(T *a, size_t ld, int J, int jb, const int32_t *ipiv, const int32_t *info, int c0a, int c1a,
-                 int c0b, int c1b, int32_t *rowid, cudaStream_t st) {
+                 int c0b, int c1b, int32_t *rowid, LaswpPlan *plan, cudaStream_t st) {
+    laswp_plan_kernel<<<1, 32, 0, st>>>(J, jb, ipiv, info, plan, rowid);
+    RLA_LAUNCHED();
     const int ncols = (c1a - c0a) + (c1b - c0b);
-    if (ncols <= 0 && rowid == nullptr) return RLA_OK;
-    // tile <= 128 KB: CW columns x 2*jb rows
-    int CW = int((128 * 1024) / (2 * size_t(jb) * sizeof(T)));
-    CW = CW >= 256 ? 256 : CW >= 128 ? 128 : CW >= 64 ? 64 : 32;
-    const size_t smem = size_t(2) * jb * CW * sizeof(T);
+    if (ncols <= 0) return RLA_OK;
+    const size_t smem = size_t(2) * jb * LASWP_CW * sizeof(T);
     static bool attr = false;
     if (!attr) {
-        RLA_CUDA(cudaFuncSetAttribute(laswp_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        RLA_CUDA(cudaFuncSetAttribute(laswp_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LASWP_MAXJB * LASWP_CW * 8));
         attr = true;
     }
-    int blocks = (ncols + CW - 1) / CW;
-    if (blocks < 1) blocks = 1;
-    laswp_kernel<T><<<blocks, LASWP_THREADS, smem, st>>>(a, ld, J, jb, ipiv, info, c0a, c1a, c0b, c1b, CW, rowid);
+    const int blocks = (ncols + LASWP_CW - 1) / LASWP_CW;
+    laswp_apply_kernel<T><<<blocks, LASWP_THREADS, smem, st>>>(a, ld, plan, info, c0a, c1a, c0b, c1b);
     RLA_LAUNCHED();
     return RLA_OK;
 }
@@ -383,19 +487,21 @@ int launch_laswp(T *a, size_t ld, int J, int jb, const int32_t *ipiv, const int3
 template <typename T>
 int launch_trsm(T *a, size_t ld, int j, int jb, int c0, int c1, const int32_t *info, cudaStream_t st) {
     if (c1 <= c0 || jb <= 1) return RLA_OK;
-    const int blocks = (c1 - c0 + TRSM_THREADS - 1) / TRSM_THREADS;
+    const int blocks = (c1 - c0 + TRSM_COLS - 1) / TRSM_COLS;
     trsm_unit_lower_kernel<T><<<blocks, TRSM_THREADS, 0, st>>>(a, ld, j, jb, c0, c1, info);
     RLA_LAUNCHED();
     return RLA_OK;
 }
 
-}  // namespace
+// scratch layout (bytes): packets | rowbuf | diagbuf | piv_log | laswp plan
+constexpr size_t SC_PACKETS = 0;
+constexpr size_t SC_ROWBUF = SC_PACKETS + 2 * GMAX * sizeof(Packet);
+constexpr size_t SC_DIAGBUF = SC_ROWBUF + size_t(2) * GMAX * PW * 8;
+constexpr size_t SC_PIVLOG = SC_DIAGBUF + 2 * PW * 8;
+constexpr size_t SC_PLAN = SC_PIVLOG + PW * 8;
+constexpr size_t SC_TOTAL = SC_PLAN + sizeof(LaswpPlan) + 256;
 
-size_t lu_scratch_bytes() {
-    // cand_abs[2][G] + cand_idx[2][G] + rowbuf[2][G][PW] + diagbuf[2][PW] + barrier word, G <= 256, T <= 8 bytes
-    const size_t G = 256;
-    return 2 * G * 8 + 2 * G * 4 + 2 * G * PW * 8 + 2 * PW * 8 + 256;
-}
+}  // namespace
 
 template <typename T>
 int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
@@ -416,23 +522,29 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         RLA_CUDA(cudaMalloc(&ws.ipiv, sizeof(int32_t) * 2 * size_t(n)));
         ws.ipiv_cap = size_t(2) * n;
     }
-    if (ws.scratch_cap < lu_scratch_bytes()) {
+    if (ws.scratch_cap < SC_TOTAL) {
         if (ws.scratch) RLA_CUDA(cudaFree(ws.scratch));
         ws.scratch = nullptr;
         ws.scratch_cap = 0;
-        RLA_CUDA(cudaMalloc(&ws.scratch, lu_scratch_bytes()));
-        ws.scratch_cap = lu_scratch_bytes();
+        RLA_CUDA(cudaMalloc(&ws.scratch, SC_TOTAL));
+        ws.scratch_cap = SC_TOTAL;
+        ws.tag = 0;
+        RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
     }
     int32_t *ipiv = ws.ipiv;
     int32_t *rowid = ws.ipiv + n;
-    const size_t GMAX = 256;
     unsigned char *sp = static_cast<unsigned char *>(ws.scratch);
-    unsigned *bar = reinterpret_cast<unsigned *>(sp);
-    T *cand_abs = reinterpret_cast<T *>(sp + 256);
-    int *cand_idx = reinterpret_cast<int *>(sp + 256 + 2 * GMAX * 8);
-    T *rowbuf = reinterpret_cast<T *>(sp + 256 + 2 * GMAX * 8 + 2 * GMAX * 4);
-    T *diagbuf = reinterpret_cast<T *>(sp + 256 + 2 * GMAX * 8 + 2 * GMAX * 4 + 2 * GMAX * PW * 8);
-    RLA_CUDA(cudaMemsetAsync(bar, 0, sizeof(unsigned), st));
+    PanelScratch sc;
+    sc.packets = reinterpret_cast<Packet *>(sp + SC_PACKETS);
+    sc.rowbuf = sp + SC_ROWBUF;
+    sc.diagbuf = sp + SC_DIAGBUF;
+    sc.piv_log = reinterpret_cast<unsigned long long *>(sp + SC_PIVLOG);
+    LaswpPlan *plan = reinterpret_cast<LaswpPlan *>(sp + SC_PLAN);
+    // tags are unique per (launch, column) for the lifetime of the scratch buffer; re-zero before wrap-around
+    if (ws.tag > 0xffffffffu - 2u * unsigned(n) - 16u) {
+        RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
+        ws.tag = 0;
+    }
     iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, n);
     RLA_LAUNCHED();
 
@@ -441,27 +553,31 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    unsigned bar_base = 0;
     for (int J0 = 0; J0 < n; J0 += OUTER_W) {
         const int w = min(OUTER_W, n - J0);
         for (int j = J0; j < J0 + w; j += PW) {
             const int jb = min(PW, J0 + w - j);
             const int nrem = n - j;
-            int G = min(g_num_sms, max(1, (nrem + 63) / 64));
+            int G = min(g_num_sms - 1, max(1, (nrem + 63) / 64));
             int R = (nrem + G - 1) / G;
             size_t smem = size_t(R) * PLDS * sizeof(T);
             if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
             {
+                // swapper CTA: interchanges of this panel applied to the rest of the outer block
+                int sw_c0a = J0, sw_c1a = j, sw_c0b = j + jb, sw_c1b = J0 + w;
+                const int swap_cols = (sw_c1a - sw_c0a) + (sw_c1b - sw_c0b);
+                const int grid = G + (swap_cols > 0 ? 1 : 0);
                 T *a_ = a;
                 size_t ld_ = ld;
-                int n__ = n, J_ = j, jb_ = jb, R_ = R;
-                void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &ipiv, &d_info, &cand_abs, &cand_idx, &rowbuf, &diagbuf, &bar, &bar_base};
-                RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(G), dim3(PANEL_THREADS), args, smem, st));
+                int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G;
+                unsigned tag_base = ws.tag;
+                void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base,
+                                &sw_c0a, &sw_c1a, &sw_c0b, &sw_c1b};
+                RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, st));
                 note_launch();
-                bar_base += unsigned(G) * unsigned(jb);
+                ws.tag += unsigned(jb);
             }
-            // interchanges inside the outer block, then U12 and the Schur update inside the block
-            RLA_TRY(launch_laswp<T>(a, ld, j, jb, ipiv, d_info, J0, j, j + jb, J0 + w, nullptr, st));
+            // U12 and the Schur update inside the outer block
             if (j + jb < J0 + w) {
                 RLA_TRY(launch_trsm<T>(a, ld, j, jb, j + jb, J0 + w, d_info, st));
                 if (j + jb < n)
@@ -471,7 +587,7 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
             }
         }
         // interchanges of the whole outer block applied left and right of it (+ the row-origin vector)
-        RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, rowid, st));
+        RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, rowid, plan, st));
         if (J0 + w < n) {
             // U12 = L11^-1 A12 by blocks of PW rows, then A22 -= L21 U12 (k = w)
             for (int kb = 0; kb < w; kb += PW) {

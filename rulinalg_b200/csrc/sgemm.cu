@@ -8,7 +8,11 @@
 //   and C stores are 256 contiguous bytes per half-row.  A and B slabs go global->shared with
 //   16-byte cp.async in a 3-stage ring, A kept in its native [m][k] orientation (row padded to
 //   20 floats so the two row groups of a warp land in different bank quads), B as [k][n].
-//   Per 4 k-steps a thread issues 8+8 LDS.128 for 256 FFMA.  Two CTAs per SM (<=128 registers).
+//   The 8x8 tile is held as 32 packed float2 accumulators (pairs along n) and updated with the
+//   Blackwell packed FP32 FMA  fma.rn.f32x2 (SASS FFMA2, scalar-broadcast A operand): two IEEE
+//   binary32 FMAs per lane per instruction, which halves the issue-slot and register-port pressure
+//   that capped the scalar-FFMA version at 58 % of the FMA pipe (ncu: dispatch stalls).  Per 4
+//   k-steps a thread issues 8+8 LDS.128 for 128 FFMA2.  Two CTAs per SM (<=128 registers).
 #include "common.cuh"
 
 namespace rla {
@@ -21,6 +25,21 @@ constexpr int A_STAGE = BM * LDAS;
 constexpr int B_STAGE = BK * LDBS;
 constexpr size_t SMEM_BYTES = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(float);
 constexpr int BAND = 16;
+
+// two independent IEEE fp32 FMAs: c.{x,y} = a.{x,y} * b.{x,y} + c.{x,y}
+__device__ __forceinline__ void ffma2(unsigned long long &c, unsigned long long a, unsigned long long b) {
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+}
+__device__ __forceinline__ unsigned long long pack2(float x, float y) {
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
+    return r;
+}
+__device__ __forceinline__ float2 unpack2(unsigned long long v) {
+    float2 r;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(r.x), "=f"(r.y) : "l"(v));
+    return r;
+}
 
 template <bool ALIGNED>
 __device__ __forceinline__ void load_slab(float *As, float *Bs, const float *__restrict__ A, size_t lda,
@@ -94,11 +113,11 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
 
-    float acc[8][8];
+    unsigned long long acc[8][4];          // acc[i][j2] = (C[i][2*j2], C[i][2*j2+1])
 #pragma unroll
     for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+        for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
 
     const int KT = (K + BK - 1) / BK;
 #pragma unroll
@@ -131,14 +150,15 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
             }
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-                const float4 b0 = *reinterpret_cast<const float4 *>(bp + (kk + q) * LDBS);
-                const float4 b1 = *reinterpret_cast<const float4 *>(bp + (kk + q) * LDBS + 64);
-                const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(bp + (kk + q) * LDBS);
+                const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(bp + (kk + q) * LDBS + 64);
+                const unsigned long long bv[4] = {b0.x, b0.y, b1.x, b1.y};
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const float av = (q == 0) ? a4[i].x : (q == 1) ? a4[i].y : (q == 2) ? a4[i].z : a4[i].w;
+                    const unsigned long long a2 = pack2(av, av);     // ptxas folds this into the .F32 broadcast operand
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av, bv[j], acc[i][j]);
+                    for (int j = 0; j < 4; ++j) ffma2(acc[i][j], a2, bv[j]);
                 }
             }
         }
@@ -155,9 +175,8 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
         for (int h = 0; h < 2; ++h) {
             const int col = n0 + h * 64 + tx * 4;
             if (col >= N) continue;
-            float v[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) v[q] = alpha * acc[i][h * 4 + q];
+            const float2 p0 = unpack2(acc[i][h * 2]), p1 = unpack2(acc[i][h * 2 + 1]);
+            float v[4] = {alpha * p0.x, alpha * p0.y, alpha * p1.x, alpha * p1.y};
             if (col + 3 < N && vec_ok) {
                 if (beta != 0.f) {
                     const float4 old = *reinterpret_cast<const float4 *>(crow + col);

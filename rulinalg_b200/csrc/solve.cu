@@ -208,17 +208,23 @@ trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int
         T va = (row0 + ra < n) ? sub_rn(__ldcg(x + row0 + ra), rsum[ra]) : T(0);
         T vb = (row0 + rb < n) ? sub_rn(__ldcg(x + row0 + rb), rsum[rb]) : T(0);
         if (LOWER) {
+#pragma unroll 8
             for (int k = 0; k < TB; ++k) {
                 const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
                 if (ra > k) va -= diag[ra * (TB + 1) + k] * xk;
                 if (rb > k) vb -= diag[rb * (TB + 1) + k] * xk;
             }
         } else {
+            // |u_ii| < eps check (mod.rs:333-336) and reciprocals for both owned rows up front, so the
+            // 64-step dependent chain below carries a multiply instead of an IEEE division
+            const T da = diag[ra * (TB + 1) + ra], db = diag[rb * (TB + 1) + rb];
+            if (row0 + ra < n && fabs(da) < EpsS<T>::v()) atomicCAS(info, 0, row0 + ra + 1);
+            if (row0 + rb < n && fabs(db) < EpsS<T>::v()) atomicCAS(info, 0, row0 + rb + 1);
+            const T ia = div_rn(T(1), da), ib = div_rn(T(1), db);
+#pragma unroll 8
             for (int k = TB - 1; k >= 0; --k) {
                 if (lane == (k & 31)) {
-                    const T d = diag[k * (TB + 1) + k];
-                    if (fabs(d) < EpsS<T>::v()) atomicCAS(info, 0, row0 + k + 1);   // mod.rs:333-336
-                    if (k < 32) va = div_rn(va, d); else vb = div_rn(vb, d);
+                    if (k < 32) va *= ia; else vb *= ib;
                 }
                 const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
                 if (ra < k) va -= diag[ra * (TB + 1) + k] * xk;

@@ -83,6 +83,26 @@ __global__ void ffma_peak(float *out, int iters, float a0, float b0) {
     if (s == 123.456f) out[0] = s;
 }
 
+// Blackwell packed fp32 FMA (fma.rn.f32x2 -> SASS FFMA2): two IEEE fp32 FMAs per lane per instruction
+template <int ILP>
+__global__ void ffma2_peak(float *out, int iters, float a0, float b0) {
+    unsigned long long c[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) c[i] = 0ull;
+    unsigned long long a, b;
+    float af = a0 + threadIdx.x * 1e-6f;
+    asm("mov.b64 %0, {%1, %1};" : "=l"(a) : "f"(af));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(b) : "f"(b0));
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(c[i]) : "l"(a), "l"(b));
+    }
+    unsigned long long s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s ^= c[i];
+    if (s == 12345ull) out[0] = 1.f;
+}
+
 // custom grid barrier: monotonically increasing counter
 __global__ void grid_barrier_lat(unsigned *counter, int rounds, long long *cycles) {
     long long t0 = clock64();
@@ -207,6 +227,22 @@ int main(int argc, char **argv) {
         }
         const double flops = 2.0 * ILP * double(iters) * threads * sms;
         printf("{\"probe\":\"ffma_peak\",\"threads_per_sm\":%d,\"ms\":%.4f,\"tflops\":%.3f}\n", threads, best,
+               flops / best * 1e-9);
+    }
+    for (int threads : {256, 512, 1024}) {
+        const int iters = 40000;
+        constexpr int ILP = 16;
+        ffma2_peak<ILP><<<sms, threads>>>((float *)dout, 100, 1.0f, 1.0f);
+        float best = 1e30f;
+        for (int rep = 0; rep < 5; ++rep) {
+            CK(cudaEventRecord(e0));
+            ffma2_peak<ILP><<<sms, threads>>>((float *)dout, iters, 1.0000001f, 1e-9f);
+            CK(cudaEventRecord(e1));
+            CK(cudaEventSynchronize(e1));
+            best = fminf(best, time_ms(e0, e1));
+        }
+        const double flops = 4.0 * ILP * double(iters) * threads * sms;
+        printf("{\"probe\":\"ffma2_peak\",\"threads_per_sm\":%d,\"ms\":%.4f,\"tflops\":%.3f}\n", threads, best,
                flops / best * 1e-9);
     }
     {

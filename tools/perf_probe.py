@@ -37,9 +37,11 @@ def main():
     out = []
     if "dgemm" in which or "sgemm" in which:
         shapes = [(n, n, n) for n in (512, 1024, 2048, 4096, 8192, 16384)] + [(65536, 256, 256), (4096, 32768, 32768), (16384, 256, 16384), (16384, 64, 192)]
-        for name, dt, fn in (("dgemm", torch.float64, l.rla_dgemm_dev), ("sgemm", torch.float32, l.rla_sgemm_dev)):
+        for name, dt, fn, cfg in (("dgemm", torch.float64, l.rla_dgemm_dev, 0), ("dgemm", torch.float64, l.rla_dgemm_dev, 1),
+                                  ("sgemm", torch.float32, l.rla_sgemm_dev, 0)):
             if name not in which:
                 continue
+            l.rla_set_tuning(b"dgemm_cfg", cfg)
             for (m, k, n) in shapes:
                 if name == "sgemm" and k == 32768:
                     continue
@@ -48,10 +50,11 @@ def main():
                 c = torch.empty(m, n, dtype=dt, device="cuda")
                 reps = 3 if m * k * n > 2e11 else 10
                 best, med = timed(lambda: rla.check(fn(m, k, n, 1.0, a.data_ptr(), k, b.data_ptr(), n, 0.0, c.data_ptr(), n, s)), reps)
-                rec = dict(op=name, m=m, k=k, n=n, ms_best=best, ms_med=med, tflops_best=2 * m * k * n / best * 1e-9, tflops_med=2 * m * k * n / med * 1e-9)
+                rec = dict(op=name, cfg=cfg, m=m, k=k, n=n, ms_best=best, ms_med=med, tflops_best=2 * m * k * n / best * 1e-9, tflops_med=2 * m * k * n / med * 1e-9)
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
                 del a, b, c
+    l.rla_set_tuning(b"dgemm_cfg", 0)
     if "lu" in which:
         for dt, fn, name in ((torch.float64, l.rla_dgetrf_dev, "dgetrf"), (torch.float32, l.rla_sgetrf_dev, "sgetrf")):
             for n in (256, 1024, 2048, 4096, 8192, 16384, 32768):
