@@ -15,6 +15,7 @@
 namespace rla {
 
 extern int g_dgemm_cfg;   // dgemm.cu
+extern int g_lu_gmax, g_lu_dbg;   // lu.cu
 
 namespace {
 
@@ -470,6 +471,15 @@ int rla_set_tuning(const char *key, int value) {
     if (strcmp(key, "dgemm_cfg") == 0) {
         if (value < 0 || value > 1) return RLA_ERR_INVALID;
         g_dgemm_cfg = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "lu_gmax") == 0) {
+        if (value < 1) return RLA_ERR_INVALID;
+        g_lu_gmax = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "lu_dbg") == 0) {
+        g_lu_dbg = value;
         return RLA_OK;
     }
     return RLA_ERR_INVALID;

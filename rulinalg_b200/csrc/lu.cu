@@ -55,92 +55,233 @@ __device__ __forceinline__ bool cand_better(T va, int ia, T vb, int ib) {
 }
 
 // -------------------------------------------------------------------------------------------
-// Panel factorisation of A[J:n, J:J+jb].  Cooperative grid of G "row" CTAs (+1 optional "swapper"
-// CTA).  Row CTA b keeps rows [J + b*R, J + (b+1)*R) of the panel in shared memory.
+// Panel factorisation of A[J:n, J:J+jb].  Cooperative grid of G "row" CTAs + 1 "hub" CTA.
+// Row CTA b keeps rows [J + b*R, J + (b+1)*R) of the panel in shared memory.
 //
-// One grid-wide exchange per column, with NO separate barrier object: every row CTA publishes a
-// 16-byte packet {|max| (f64), row index, tag} -- preceded by the candidate row's contents -- and
-// then polls the G packets until all carry the tag of this column; the data arrival IS the barrier.
-// Tags are unique per (panel launch, column), buffers alternate by column parity: a CTA can only be
-// one column ahead of the slowest one, because it needs everybody's packet to advance.
+// One grid-wide exchange per column, through 16-byte self-validating messages {payload, tag}
+// (tags are unique per (panel launch, column); a 16-byte aligned store is single-copy atomic, so no
+// fence is needed between a message and the data it announces -- every piece carries its own tag):
+//   row CTA  -> candidate packet {|max|, row index, tag} + the candidate row as 64 tagged chunks
+//   hub CTA  -> polls the G packets with G threads (the only heavy poller in the grid), reduces, and
+//               publishes ONE result message {pivot row, winning CTA, singular flag, tag}
+//   row CTAs -> one thread polls the result, then 64 threads fetch the winner's tagged row chunks.
+// Buffers alternate by column parity; a row CTA can be at most one column ahead of the slowest one
+// because the hub needs every packet to publish the next result.
 //
-// The swapper CTA never publishes, so nobody waits for it: it follows the pivot log written by CTA 0
-// and applies each interchange to the columns of the enclosing outer block that lie outside this
-// panel (what used to be a separate, latency-bound "inner laswp" launch).
+// The hub's remaining warps use the pivots as they are decided: one warp folds each interchange into
+// the outer block's net-permutation plan (consumed by laswp_apply_kernel), ten warps apply it to the
+// columns of the outer block that lie outside this panel.  Nobody ever waits for them.
 // -------------------------------------------------------------------------------------------
-struct __align__(16) Packet {
-    double absval;
-    int idx;
-    unsigned tag;
+struct __align__(16) Msg {
+    unsigned long long lo, hi;
 };
-__device__ __forceinline__ void packet_store(Packet *p, double a, int idx, unsigned tag) {
-    const unsigned long long lo = (unsigned long long)__double_as_longlong(a);
-    const unsigned long long hi = (unsigned long long)(unsigned)idx | ((unsigned long long)tag << 32);
+__device__ __forceinline__ void msg_store(Msg *p, unsigned long long lo, unsigned long long hi) {
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(p), "l"(lo), "l"(hi) : "memory");
 }
-__device__ __forceinline__ void packet_load(const Packet *p, double &a, int &idx, unsigned &tag) {
-    unsigned long long lo, hi;
+__device__ __forceinline__ void msg_load(const Msg *p, unsigned long long &lo, unsigned long long &hi) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
-    a = __longlong_as_double((long long)lo);
-    idx = int(unsigned(hi & 0xffffffffull));
-    tag = unsigned(hi >> 32);
 }
+__device__ __forceinline__ unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
+__device__ __forceinline__ unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
+__device__ __forceinline__ void from_bits(unsigned long long b, double &v) { v = __longlong_as_double((long long)b); }
+__device__ __forceinline__ void from_bits(unsigned long long b, float &v) { v = __uint_as_float(unsigned(b)); }
 
-struct PanelScratch {
-    Packet *packets;                 // [2][GMAX]
-    void *rowbuf;                    // [2][GMAX][PW] of T
-    void *diagbuf;                   // [2][PW] of T
-    unsigned long long *piv_log;     // [PW]  (tag << 32 | pivot row) written by CTA 0
-};
 constexpr int GMAX = 256;
+constexpr int LASWP_MAXJB = OUTER_W;
+// Net effect of an outer block's interchanges, built incrementally by the hub CTA.
+//   "Touched" rows: index i < w -> row J0+i; index w+f -> far row fr[f].  origin[i] = touched index
+//   whose OLD contents end up in touched row i.
+struct LaswpPlan {
+    int nt;
+    int rows[2 * LASWP_MAXJB];
+    int origin[2 * LASWP_MAXJB];
+};
+struct PlanState {
+    int nf;
+    int od[LASWP_MAXJB];             // origin of dense touched rows
+    int fr[LASWP_MAXJB];             // far row numbers
+    int of[LASWP_MAXJB];             // origin of far touched rows
+};
+struct PanelScratch {
+    Msg *packets;                    // [2][GMAX]       {bits(|max| as f64), idx | tag<<32}
+    Msg *rowbuf;                     // [2][GMAX][PW]   {bits(value), tag}
+    Msg *diagbuf;                    // [2][PW]         {bits(value), tag}
+    Msg *result;                     // [2]             {pivot idx | win<<32, singular | tag<<32}
+    PlanState *state;
+    LaswpPlan *plan;
+    int32_t *rowid;
+};
+constexpr int HUB_ROOT_WARPS = 5;                 // 160 threads >= G
+constexpr int HUB_ROOT_THREADS = HUB_ROOT_WARPS * 32;
+constexpr int HUB_SWAP_T0 = 192;                  // warps 6..15 apply the interchanges
 
 template <typename T>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G, int32_t *__restrict__ ipiv,
-                int32_t *__restrict__ info, PanelScratch sc, unsigned tag_base, int sw_c0a, int sw_c1a, int sw_c0b,
-                int sw_c1b) {
+                int32_t *__restrict__ info, PanelScratch sc, unsigned tag_base, int J0, int w, int dbg) {
     if (*info != 0) return;   // an earlier panel hit a tiny pivot: written by a previous kernel => uniform
     extern __shared__ __align__(16) unsigned char panel_smem[];
     T *s = reinterpret_cast<T *>(panel_smem);
     __shared__ T prow_s[PW];
-    __shared__ T red_abs[PANEL_THREADS / 32];
-    __shared__ int red_idx[PANEL_THREADS / 32];
+    __shared__ T red_abs[2][PANEL_THREADS / 32];
+    __shared__ int red_idx[2][PANEL_THREADS / 32];
+    __shared__ int red_win[2][PANEL_THREADS / 32];
     __shared__ T sh_abs;
-    __shared__ int sh_idx, sh_win;
+    __shared__ int sh_idx, sh_win, sh_sing;
+    __shared__ int piv_sm[PW];
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    T *rowbuf = static_cast<T *>(sc.rowbuf);
-    T *diagbuf = static_cast<T *>(sc.diagbuf);
 
     if (b >= G) {
-        // ---------------- swapper CTA ----------------
-        const int na = sw_c1a - sw_c0a, ncols = na + (sw_c1b - sw_c0b);
-        const int col = (tid < na) ? sw_c0a + tid : sw_c0b + (tid - na);
-        for (int c = 0; c < jb; ++c) {
-            if (tid == 0) {
-                const unsigned want = tag_base + unsigned(c) + 1u;
-                unsigned long long v;
-                do {
-                    v = *((volatile unsigned long long *)(sc.piv_log + c));
-                } while (unsigned(v >> 32) != want);
-                sh_idx = int(unsigned(v & 0xffffffffull));
+        // =========================== hub CTA ===========================
+        __shared__ PlanState st;
+        const bool first = (J == J0), last = (J + jb == J0 + w);
+        if (first) {
+            for (int i = tid; i < w; i += PANEL_THREADS) st.od[i] = i;
+            if (tid == 0) st.nf = 0;
+        } else {
+            for (int i = tid; i < LASWP_MAXJB; i += PANEL_THREADS) {
+                st.od[i] = sc.state->od[i];
+                st.fr[i] = sc.state->fr[i];
+                st.of[i] = sc.state->of[i];
             }
-            __syncthreads();
-            const int p = sh_idx;
-            __syncthreads();
-            if (p < 0) return;                       // singular: CTA 0 logged -1
+            if (tid == 0) st.nf = sc.state->nf;
+        }
+        for (int i = tid; i < PW; i += PANEL_THREADS) piv_sm[i] = INT_MIN;
+        __syncthreads();
+
+        if (warp < HUB_ROOT_WARPS) {
+            // ---- root: gather G candidate packets, reduce, publish the result ----
+            for (int c = 0; c < jb; ++c) {
+                const int par = c & 1;
+                const unsigned tag = tag_base + unsigned(c) + 1u;
+                T gv = T(-1);
+                int gi = INT_MAX, gw = 0;
+                // whole warps poll: lanes past G re-read packet G-1 (a duplicate candidate is harmless),
+                // so no polling warp is ever partially active
+                if ((tid & ~31) < G) {
+                    const int q = min(tid, G - 1);
+                    unsigned long long lo, hi;
+                    do {
+                        msg_load(sc.packets + par * GMAX + q, lo, hi);
+                    } while (unsigned(hi >> 32) != tag);
+                    gv = T(__longlong_as_double((long long)lo));
+                    gi = int(unsigned(hi & 0xffffffffull));
+                    gw = q;
+                }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) {
+                    const T ov = __shfl_down_sync(0xffffffffu, gv, off);
+                    const int oi = __shfl_down_sync(0xffffffffu, gi, off);
+                    const int ow = __shfl_down_sync(0xffffffffu, gw, off);
+                    if (cand_better(ov, oi, gv, gi)) { gv = ov; gi = oi; gw = ow; }
+                }
+                if (lane == 0) { red_abs[par][warp] = gv; red_idx[par][warp] = gi; red_win[par][warp] = gw; }
+                asm volatile("bar.sync 1, %0;" ::"n"(HUB_ROOT_THREADS) : "memory");
+                int sing = 0;
+                if (warp == 0) {
+                    gv = (lane < HUB_ROOT_WARPS) ? red_abs[par][lane] : T(-1);
+                    gi = (lane < HUB_ROOT_WARPS) ? red_idx[par][lane] : INT_MAX;
+                    gw = (lane < HUB_ROOT_WARPS) ? red_win[par][lane] : 0;
+#pragma unroll
+                    for (int off = 4; off > 0; off >>= 1) {
+                        const T ov = __shfl_down_sync(0xffffffffu, gv, off);
+                        const int oi = __shfl_down_sync(0xffffffffu, gi, off);
+                        const int ow = __shfl_down_sync(0xffffffffu, gw, off);
+                        if (cand_better(ov, oi, gv, gi)) { gv = ov; gi = oi; gw = ow; }
+                    }
+                    if (lane == 0) {
+                        sing = (gv < Eps<T>::v()) ? 1 : 0;         // lu.rs:179-183 (NaN: false, continues)
+                        msg_store(sc.result + par, (unsigned long long)(unsigned)gi | ((unsigned long long)(unsigned)gw << 32),
+                                  (unsigned long long)sing | ((unsigned long long)tag << 32));
+                        if (sing) {
+                            *info = J + c + 1;
+                        } else {
+                            ipiv[J + c] = gi;
+                        }
+                        *((volatile int *)&piv_sm[c]) = sing ? -1 : gi;
+                    }
+                    sing = __shfl_sync(0xffffffffu, sing, 0);
+                    if (lane == 0) sh_sing = sing;
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(HUB_ROOT_THREADS) : "memory");
+                if (*((volatile int *)&sh_sing) && *((volatile int *)&piv_sm[c]) == -1) return;
+            }
+            return;
+        }
+
+        // ---- workers: follow the pivots through shared memory ----
+        const int sw_c0a = J0, sw_c1a = J, sw_c0b = J + jb, sw_c1b = J0 + w;
+        const int na = sw_c1a - sw_c0a, ncols = na + (sw_c1b - sw_c0b);
+        const int t2 = tid - HUB_SWAP_T0;
+        const int col = (t2 < na) ? sw_c0a + t2 : sw_c0b + (t2 - na);
+        int nf = st.nf;
+        if (warp != HUB_ROOT_WARPS && (t2 < 0 || t2 >= ncols)) return;
+        for (int c = 0; c < jb; ++c) {
+            int p;
+            while ((p = *((volatile int *)&piv_sm[c])) == INT_MIN) {
+            }
+            if (p < 0) return;                       // singular
             const int d = J + c;
-            if (p != d && tid < ncols) {
+            if (p == d) continue;
+            if (warp == HUB_ROOT_WARPS) {
+                // plan warp
+                const int k = d - J0;                // dense index of the diagonal row
+                if (p < J0 + w) {
+                    if (lane == 0) { const int t = st.od[k]; st.od[k] = st.od[p - J0]; st.od[p - J0] = t; }
+                } else {
+                    int f = -1;
+                    for (int base = 0; base < nf; base += 32) {
+                        const int q = base + lane;
+                        const unsigned hit = __ballot_sync(0xffffffffu, q < nf && st.fr[q] == p);
+                        if (hit) { f = base + __ffs(hit) - 1; break; }
+                    }
+                    if (f < 0) {
+                        f = nf++;
+                        if (lane == 0) { st.fr[f] = p; st.of[f] = w + f; }
+                    }
+                    __syncwarp();
+                    if (lane == 0) { const int t = st.od[k]; st.od[k] = st.of[f]; st.of[f] = t; }
+                }
+                __syncwarp();
+            } else if (!(dbg & 1)) {
                 T *rd = A + size_t(d) * ld + col, *rp = A + size_t(p) * ld + col;
                 const T vd = *rd, vp = *rp;
                 *rd = vp;
                 *rp = vd;
             }
         }
+        if (warp == HUB_ROOT_WARPS) {
+            if (!last) {
+                for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                    sc.state->od[i] = st.od[i];
+                    sc.state->fr[i] = st.fr[i];
+                    sc.state->of[i] = st.of[i];
+                }
+                if (lane == 0) sc.state->nf = nf;
+            } else {
+                // outer block complete: publish the plan and permute the row-origin vector
+                const int nt = w + nf;
+                int *ids = reinterpret_cast<int *>(panel_smem);
+                if (lane == 0) sc.plan->nt = nt;
+                for (int i = lane; i < nt; i += 32) {
+                    const int row = (i < w) ? J0 + i : st.fr[i - w];
+                    sc.plan->rows[i] = row;
+                    sc.plan->origin[i] = (i < w) ? st.od[i] : st.of[i - w];
+                    ids[i] = sc.rowid[row];
+                }
+                __syncwarp();
+                for (int i = lane; i < nt; i += 32) {
+                    const int o = (i < w) ? st.od[i] : st.of[i - w];
+                    if (o != i) sc.rowid[(i < w) ? J0 + i : st.fr[i - w]] = ids[o];
+                }
+            }
+        }
         return;
     }
 
+    // =========================== row CTAs ===========================
     const int r0 = J + b * R;
     const int r1 = min(n, r0 + R);
     const int nrows = max(0, r1 - r0);
@@ -155,6 +296,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int d = J + c;                       // global diagonal row of this column
         const int par = c & 1;
         const unsigned tag = tag_base + unsigned(c) + 1u;
+        const unsigned long long tag_hi = (unsigned long long)tag << 32;
         const int lo = max(0, d - r0);             // first local row still active
         const bool owns_d = (d >= r0 && d < r1);
 
@@ -171,11 +313,11 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             const int oi = __shfl_down_sync(0xffffffffu, bidx, off);
             if (cand_better(ov, oi, best, bidx)) { best = ov; bidx = oi; }
         }
-        if (lane == 0) { red_abs[warp] = best; red_idx[warp] = bidx; }
+        if (lane == 0) { red_abs[0][warp] = best; red_idx[0][warp] = bidx; }
         __syncthreads();
         if (warp == 0) {
-            best = (lane < PANEL_THREADS / 32) ? red_abs[lane] : T(-1);
-            bidx = (lane < PANEL_THREADS / 32) ? red_idx[lane] : INT_MAX;
+            best = (lane < PANEL_THREADS / 32) ? red_abs[0][lane] : T(-1);
+            bidx = (lane < PANEL_THREADS / 32) ? red_idx[0][lane] : INT_MAX;
 #pragma unroll
             for (int off = 8; off > 0; off >>= 1) {
                 const T ov = __shfl_down_sync(0xffffffffu, best, off);
@@ -189,72 +331,60 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                     const T dv = s[(d - r0) * PLDS + c];
                     if (dv != dv) { best = inf_of(T(0)); bidx = d; }
                 }
-                sh_abs = best;
                 sh_idx = bidx;
+                // candidate packet first: it is what the hub is waiting for
+                msg_store(sc.packets + par * GMAX + b, bits_of(double(best)), (unsigned long long)(unsigned)bidx | tag_hi);
             }
         }
         __syncthreads();
-        // ---- publish: candidate row (and the diagonal row) first, then the tagged packet ----
+        // ---- candidate row (and the diagonal row) as self-validating chunks ----
         {
             const int li = sh_idx;
-            if (li != INT_MAX && tid < jb) {
-                rowbuf[size_t(par * GMAX + b) * PW + tid] = s[(li - r0) * PLDS + tid];
-                __threadfence();
-            }
-            if (owns_d && tid >= 64 && tid < 64 + jb) {
-                diagbuf[par * PW + (tid - 64)] = s[(d - r0) * PLDS + (tid - 64)];
-                __threadfence();
-            }
+            if (li != INT_MAX && tid < jb)
+                msg_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(s[(li - r0) * PLDS + tid]), tag_hi);
+            if (owns_d && tid >= 64 && tid < 64 + jb)
+                msg_store(sc.diagbuf + par * PW + (tid - 64), bits_of(s[(d - r0) * PLDS + (tid - 64)]), tag_hi);
         }
-        __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            packet_store(sc.packets + par * GMAX + b, double(sh_abs), sh_idx, tag);
-        }
-        // ---- gather: poll all G packets of this column, reduce (every CTA, redundantly) ----
+        // ---- wait for the hub's verdict ----
         if (warp == 0) {
-            T gv = T(-1);
-            int gi = INT_MAX, gw = 0;
-            for (int q = lane; q < G; q += 32) {
-                double a;
-                int i;
-                unsigned tg;
-                do {
-                    packet_load(sc.packets + par * GMAX + q, a, i, tg);
-                } while (tg != tag);
-                const T v = T(a);
-                if (cand_better(v, i, gv, gi)) { gv = v; gi = i; gw = q; }
+            // the WHOLE warp polls the same address: a spin loop in a partially active warp is several
+            // times slower on this part (measured: 5.4 vs 3.1 us per column)
+            unsigned long long rlo, rhi;
+            do {
+                msg_load(sc.result + par, rlo, rhi);
+            } while (unsigned(rhi >> 32) != tag);
+            if (lane == 0) {
+                sh_idx = int(unsigned(rlo & 0xffffffffull));
+                sh_win = int(unsigned(rlo >> 32));
+                sh_sing = int(rhi & 1ull);
             }
-            __threadfence();
-#pragma unroll
-            for (int off = 16; off > 0; off >>= 1) {
-                const T ov = __shfl_down_sync(0xffffffffu, gv, off);
-                const int oi = __shfl_down_sync(0xffffffffu, gi, off);
-                const int ow = __shfl_down_sync(0xffffffffu, gw, off);
-                if (cand_better(ov, oi, gv, gi)) { gv = ov; gi = oi; gw = ow; }
-            }
-            if (lane == 0) { sh_abs = gv; sh_idx = gi; sh_win = gw; }
         }
         __syncthreads();
-        const T pabs = sh_abs;
         const int prow_idx = sh_idx, win = sh_win;
-        if (pabs < Eps<T>::v()) {                  // lu.rs:179-183 (NaN: comparison false, continues)
-            if (b == 0 && tid == 0) {
-                *info = d + 1;
-                sc.piv_log[c] = ((unsigned long long)tag << 32) | 0xffffffffull;   // tell the swapper to stop
-            }
-            return;                                // uniform across the grid
-        }
-        if (tid < jb) prow_s[tid] = __ldcg(rowbuf + size_t(par * GMAX + win) * PW + tid);
-        if (b == 0 && tid == 0) {
-            ipiv[d] = prow_idx;
-            sc.piv_log[c] = ((unsigned long long)tag << 32) | (unsigned long long)(unsigned)prow_idx;
+        if (sh_sing) return;                       // uniform across the grid; the hub set *info
+        if ((tid & ~31) < jb) {                   // whole warps poll (lanes past jb re-read chunk jb-1)
+            unsigned long long vlo, vhi;
+            const Msg *src = sc.rowbuf + size_t(par * GMAX + win) * PW + min(tid, jb - 1);
+            do {
+                msg_load(src, vlo, vhi);
+            } while (unsigned(vhi >> 32) != tag);
+            T v;
+            from_bits(vlo, v);
+            if (tid < jb) prow_s[tid] = v;
         }
         __syncthreads();
         if (prow_idx != d) {                       // swap rows d <-> prow_idx inside the panel
             if (owns_d && tid < jb) s[(d - r0) * PLDS + tid] = prow_s[tid];
-            if (prow_idx >= r0 && prow_idx < r1 && tid >= 64 && tid < 64 + jb)
-                s[(prow_idx - r0) * PLDS + (tid - 64)] = __ldcg(diagbuf + par * PW + (tid - 64));
+            if (prow_idx >= r0 && prow_idx < r1 && tid >= 64 && ((tid - 64) & ~31) < jb) {
+                unsigned long long vlo, vhi;
+                const Msg *src = sc.diagbuf + par * PW + min(tid - 64, jb - 1);
+                do {
+                    msg_load(src, vlo, vhi);
+                } while (unsigned(vhi >> 32) != tag);
+                T v;
+                from_bits(vlo, v);
+                if (tid - 64 < jb) s[(prow_idx - r0) * PLDS + (tid - 64)] = v;
+            }
             __syncthreads();
         }
         // ---- multipliers (one IEEE division per row), then rank-1 update with mul, sub ----
@@ -287,65 +417,6 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
 //   apply kernel: each CTA owns 32 columns; reads every source row segment into shared memory
 //     (8 independent loads in flight per lane), then writes the destinations.
 // -------------------------------------------------------------------------------------------
-constexpr int LASWP_MAXJB = OUTER_W;
-struct LaswpPlan {
-    int nt;
-    int rows[2 * LASWP_MAXJB];
-    int origin[2 * LASWP_MAXJB];
-};
-
-__global__ void __launch_bounds__(32)
-laswp_plan_kernel(int J, int jb, const int32_t *__restrict__ ipiv, const int32_t *__restrict__ info,
-                  LaswpPlan *__restrict__ plan, int32_t *__restrict__ rowid) {
-    if (*info != 0) return;
-    __shared__ int od[LASWP_MAXJB];       // origin of dense touched rows
-    __shared__ int fr[LASWP_MAXJB];       // far row numbers
-    __shared__ int of[LASWP_MAXJB];       // origin of far touched rows
-    __shared__ int piv_s[LASWP_MAXJB];
-    __shared__ int ids[2 * LASWP_MAXJB];
-    const int lane = threadIdx.x;
-    for (int i = lane; i < jb; i += 32) {
-        od[i] = i;
-        piv_s[i] = ipiv[J + i];
-    }
-    __syncwarp();
-    int nf = 0;
-    for (int k = 0; k < jb; ++k) {
-        const int bq = piv_s[k];
-        if (bq == J + k) continue;
-        if (bq < J + jb) {
-            if (lane == 0) { const int t = od[k]; od[k] = od[bq - J]; od[bq - J] = t; }
-        } else {
-            int f = -1;
-            for (int base = 0; base < nf; base += 32) {
-                const int q = base + lane;
-                const unsigned hit = __ballot_sync(0xffffffffu, q < nf && fr[q] == bq);
-                if (hit) { f = base + __ffs(hit) - 1; break; }
-            }
-            if (f < 0) {
-                f = nf++;
-                if (lane == 0) { fr[f] = bq; of[f] = jb + f; }
-            }
-            __syncwarp();
-            if (lane == 0) { const int t = od[k]; od[k] = of[f]; of[f] = t; }
-        }
-        __syncwarp();
-    }
-    const int nt = jb + nf;
-    if (lane == 0) plan->nt = nt;
-    for (int i = lane; i < nt; i += 32) {
-        plan->rows[i] = (i < jb) ? J + i : fr[i - jb];
-        plan->origin[i] = (i < jb) ? od[i] : of[i - jb];
-    }
-    // the row-origin vector rides along
-    for (int i = lane; i < nt; i += 32) ids[i] = rowid[(i < jb) ? J + i : fr[i - jb]];
-    __syncwarp();
-    for (int i = lane; i < nt; i += 32) {
-        const int o = (i < jb) ? od[i] : of[i - jb];
-        if (o != i) rowid[(i < jb) ? J + i : fr[i - jb]] = ids[o];
-    }
-}
-
 constexpr int LASWP_THREADS = 512;
 constexpr int LASWP_CW = 32;
 
@@ -467,9 +538,8 @@ int g_num_sms = 0;
 
 template <typename T>
 int launch_laswp(T *a, size_t ld, int J, int jb, const int32_t *ipiv, const int32_t *info, int c0a, int c1a,
-                 int c0b, int c1b, int32_t *rowid, LaswpPlan *plan, cudaStream_t st) {
-    laswp_plan_kernel<<<1, 32, 0, st>>>(J, jb, ipiv, info, plan, rowid);
-    RLA_LAUNCHED();
+                 int c0b, int c1b, LaswpPlan *plan, cudaStream_t st) {
+    (void)J; (void)ipiv;
     const int ncols = (c1a - c0a) + (c1b - c0b);
     if (ncols <= 0) return RLA_OK;
     const size_t smem = size_t(2) * jb * LASWP_CW * sizeof(T);
@@ -493,15 +563,19 @@ int launch_trsm(T *a, size_t ld, int j, int jb, int c0, int c1, const int32_t *i
     return RLA_OK;
 }
 
-// scratch layout (bytes): packets | rowbuf | diagbuf | piv_log | laswp plan
+// scratch layout (bytes): packets | rowbuf | diagbuf | result | laswp plan | plan state
 constexpr size_t SC_PACKETS = 0;
-constexpr size_t SC_ROWBUF = SC_PACKETS + 2 * GMAX * sizeof(Packet);
-constexpr size_t SC_DIAGBUF = SC_ROWBUF + size_t(2) * GMAX * PW * 8;
-constexpr size_t SC_PIVLOG = SC_DIAGBUF + 2 * PW * 8;
-constexpr size_t SC_PLAN = SC_PIVLOG + PW * 8;
-constexpr size_t SC_TOTAL = SC_PLAN + sizeof(LaswpPlan) + 256;
+constexpr size_t SC_ROWBUF = SC_PACKETS + 2 * GMAX * sizeof(Msg);
+constexpr size_t SC_DIAGBUF = SC_ROWBUF + size_t(2) * GMAX * PW * sizeof(Msg);
+constexpr size_t SC_RESULT = SC_DIAGBUF + 2 * PW * sizeof(Msg);
+constexpr size_t SC_PLAN = SC_RESULT + 256;
+constexpr size_t SC_STATE = SC_PLAN + ((sizeof(LaswpPlan) + 255) / 256) * 256;
+constexpr size_t SC_TOTAL = SC_STATE + sizeof(PlanState) + 256;
 
 }  // namespace
+
+int g_lu_gmax = 1 << 30;      // rla_set_tuning("lu_gmax", v): cap on the number of row CTAs of the panel kernel
+int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): timing experiments only (bit0: hub skips the row swaps)
 
 template <typename T>
 int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
@@ -535,11 +609,14 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
     int32_t *rowid = ws.ipiv + n;
     unsigned char *sp = static_cast<unsigned char *>(ws.scratch);
     PanelScratch sc;
-    sc.packets = reinterpret_cast<Packet *>(sp + SC_PACKETS);
-    sc.rowbuf = sp + SC_ROWBUF;
-    sc.diagbuf = sp + SC_DIAGBUF;
-    sc.piv_log = reinterpret_cast<unsigned long long *>(sp + SC_PIVLOG);
+    sc.packets = reinterpret_cast<Msg *>(sp + SC_PACKETS);
+    sc.rowbuf = reinterpret_cast<Msg *>(sp + SC_ROWBUF);
+    sc.diagbuf = reinterpret_cast<Msg *>(sp + SC_DIAGBUF);
+    sc.result = reinterpret_cast<Msg *>(sp + SC_RESULT);
     LaswpPlan *plan = reinterpret_cast<LaswpPlan *>(sp + SC_PLAN);
+    sc.plan = plan;
+    sc.state = reinterpret_cast<PlanState *>(sp + SC_STATE);
+    sc.rowid = rowid;
     // tags are unique per (launch, column) for the lifetime of the scratch buffer; re-zero before wrap-around
     if (ws.tag > 0xffffffffu - 2u * unsigned(n) - 16u) {
         RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
@@ -558,21 +635,21 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         for (int j = J0; j < J0 + w; j += PW) {
             const int jb = min(PW, J0 + w - j);
             const int nrem = n - j;
-            int G = min(g_num_sms - 1, max(1, (nrem + 63) / 64));
+            int G = min(min(min(g_num_sms - 1, HUB_ROOT_THREADS), g_lu_gmax), max(1, (nrem + 63) / 64));
+            while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
             int R = (nrem + G - 1) / G;
             size_t smem = size_t(R) * PLDS * sizeof(T);
+            if (smem < 2 * LASWP_MAXJB * sizeof(int)) smem = 2 * LASWP_MAXJB * sizeof(int);   // swapper's id scratch
             if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
             {
-                // swapper CTA: interchanges of this panel applied to the rest of the outer block
-                int sw_c0a = J0, sw_c1a = j, sw_c0b = j + jb, sw_c1b = J0 + w;
-                const int swap_cols = (sw_c1a - sw_c0a) + (sw_c1b - sw_c0b);
-                const int grid = G + (swap_cols > 0 ? 1 : 0);
+                // +1 swapper CTA: interchanges of this panel applied to the rest of the outer block, and the
+                // outer block's net permutation plan (consumed by laswp_apply_kernel) built on the fly
+                const int grid = G + 1;
                 T *a_ = a;
                 size_t ld_ = ld;
-                int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G;
+                int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G, J0_ = J0, w_ = w, dbg_ = g_lu_dbg;
                 unsigned tag_base = ws.tag;
-                void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base,
-                                &sw_c0a, &sw_c1a, &sw_c0b, &sw_c1b};
+                void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base, &J0_, &w_, &dbg_};
                 RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, st));
                 note_launch();
                 ws.tag += unsigned(jb);
@@ -587,7 +664,7 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
             }
         }
         // interchanges of the whole outer block applied left and right of it (+ the row-origin vector)
-        RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, rowid, plan, st));
+        RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, plan, st));
         if (J0 + w < n) {
             // U12 = L11^-1 A12 by blocks of PW rows, then A22 -= L21 U12 (k = w)
             for (int kb = 0; kb < w; kb += PW) {

@@ -172,13 +172,11 @@ trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int
     for (int t = 0; t < nd; ++t) {
         const int Jb = LOWER ? t : nblk - 1 - t;
         if (seen < t + 1) {
-            if (lane == 0) {
-                int s;
-                while ((s = *done) < t + 1) {
-                }
-                seen = s;
+            // whole warp polls (a spin loop in a partially active warp is several times slower)
+            int s;
+            while ((s = *done) < t + 1) {
             }
-            seen = __shfl_sync(0xffffffffu, seen, 0);
+            seen = __shfl_sync(0xffffffffu, s, 0);
             __threadfence();
         }
         const int col = Jb * TB + 2 * lane;
