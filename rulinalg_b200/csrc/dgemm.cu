@@ -302,7 +302,7 @@ int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size
 
 }  // namespace
 
-int g_dgemm_cfg = 0;   // 0 = 128x64 (2 CTAs/SM), 1 = 128x128 (1 CTA/SM); rla_set_tuning("dgemm_cfg", v)
+int g_dgemm_cfg = -1;  // -1 = auto, 0 = 128x64 (2 CTAs/SM), 1 = 128x128 (1 CTA/SM); rla_set_tuning("dgemm_cfg", v)
 
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st) {
@@ -325,7 +325,11 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     const bool aligned = ((lda & 1) == 0) && ((ldb & 1) == 0) &&
                          ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
-    if (g_dgemm_cfg == 1) {
+    // -1 (default): 128x128 tiles for long-k products that fill the machine several times over (2 % faster
+    // there), the 2-CTA/SM 128x64 shape otherwise (rank-k updates, small and skinny products)
+    int cfg = g_dgemm_cfg;
+    if (cfg < 0) cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? 1 : 0;
+    if (cfg == 1) {
         return aligned ? launch_cfg<CfgLarge, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                        : launch_cfg<CfgLarge, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     }

@@ -1,0 +1,47 @@
+//! src/ffi.rs -- bindings to librla_b200 (include/rla_b200.h).  Added to rulinalg by the integration;
+//! `mod ffi;` goes into src/lib.rs next to `extern crate matrixmultiply;` (src/lib.rs:90).
+#![allow(non_camel_case_types)]
+
+use error::{Error, ErrorKind};
+
+pub const RLA_OK: i32 = 0;
+pub const RLA_ERR_SINGULAR: i32 = 1;
+
+#[repr(C)]
+pub struct rla_lu_handle {
+    _private: [u8; 0],
+}
+
+extern "C" {
+    /// Same argument order and meaning as matrixmultiply::dgemm (src/matrix/mat_mul.rs:57-67).
+    pub fn rla_dgemm(m: usize, k: usize, n: usize, alpha: f64,
+                     a: *const f64, rsa: isize, csa: isize,
+                     b: *const f64, rsb: isize, csb: isize,
+                     beta: f64, c: *mut f64, rsc: isize, csc: isize) -> i32;
+    /// Same as matrixmultiply::sgemm (src/matrix/mat_mul.rs:33-43).
+    pub fn rla_sgemm(m: usize, k: usize, n: usize, alpha: f32,
+                     a: *const f32, rsa: isize, csa: isize,
+                     b: *const f32, rsb: isize, csb: isize,
+                     beta: f32, c: *mut f32, rsc: isize, csc: isize) -> i32;
+    pub fn rla_dgetrf(n: usize, lu: *mut f64, perm: *mut usize) -> i32;
+    pub fn rla_sgetrf(n: usize, lu: *mut f32, perm: *mut usize) -> i32;
+    pub fn rla_dgetrs(n: usize, lu: *const f64, perm: *const usize, b: *mut f64) -> i32;
+    pub fn rla_sgetrs(n: usize, lu: *const f32, perm: *const usize, b: *mut f32) -> i32;
+    pub fn rla_dgetrf_keep(n: usize, lu: *mut f64, perm: *mut usize, out: *mut *mut rla_lu_handle) -> i32;
+    pub fn rla_dlu_solve(h: *const rla_lu_handle, b: *mut f64) -> i32;
+    pub fn rla_lu_free(h: *mut rla_lu_handle);
+    pub fn rla_strerror(status: i32) -> *const ::std::os::raw::c_char;
+}
+
+/// Numerical statuses become `Err(Error)`, environment failures (no device, CUDA error) panic:
+/// north_star forbids a CPU fallback, and the reference has no error kind for them.
+pub fn check(status: i32, singular_msg: &'static str) -> Result<(), Error> {
+    match status {
+        RLA_OK => Ok(()),
+        RLA_ERR_SINGULAR => Err(Error::new(ErrorKind::DivByZero, singular_msg)),
+        s => {
+            let msg = unsafe { ::std::ffi::CStr::from_ptr(rla_strerror(s)) };
+            panic!("librla_b200: status {} ({})", s, msg.to_string_lossy())
+        }
+    }
+}
