@@ -51,6 +51,8 @@ struct LuWorkspace {
     void *scratch = nullptr;      // panel scratch (candidates, barrier words, row buffers)
     size_t ipiv_cap = 0, scratch_cap = 0;
     unsigned tag = 0;             // next free packet tag (unique per panel column while scratch lives)
+    cudaStream_t side = nullptr;  // high-priority stream for the look-ahead panel factorisation
+    cudaEvent_t ev_head = nullptr, ev_fact = nullptr;
 };
 template <typename T>
 int getrf_launch(size_t n, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws,

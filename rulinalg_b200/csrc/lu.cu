@@ -630,7 +630,8 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    for (int J0 = 0; J0 < n; J0 += OUTER_W) {
+    // factor the 256-column outer block at J0 (its columns must already carry every earlier Schur update)
+    auto factor_block = [&](int J0, cudaStream_t s) -> int {
         const int w = min(OUTER_W, n - J0);
         for (int j = J0; j < J0 + w; j += PW) {
             const int jb = min(PW, J0 + w - j);
@@ -639,45 +640,79 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
             while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
             int R = (nrem + G - 1) / G;
             size_t smem = size_t(R) * PLDS * sizeof(T);
-            if (smem < 2 * LASWP_MAXJB * sizeof(int)) smem = 2 * LASWP_MAXJB * sizeof(int);   // swapper's id scratch
+            if (smem < 2 * LASWP_MAXJB * sizeof(int)) smem = 2 * LASWP_MAXJB * sizeof(int);   // hub's id scratch
             if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
             {
-                // +1 swapper CTA: interchanges of this panel applied to the rest of the outer block, and the
-                // outer block's net permutation plan (consumed by laswp_apply_kernel) built on the fly
+                // +1 hub CTA: reduces the candidates, applies the interchanges to the rest of the outer block and
+                // builds the outer block's net permutation plan (consumed by laswp_apply_kernel) on the fly
                 const int grid = G + 1;
                 T *a_ = a;
                 size_t ld_ = ld;
                 int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G, J0_ = J0, w_ = w, dbg_ = g_lu_dbg;
                 unsigned tag_base = ws.tag;
                 void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base, &J0_, &w_, &dbg_};
-                RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, st));
+                RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, s));
                 note_launch();
                 ws.tag += unsigned(jb);
             }
             // U12 and the Schur update inside the outer block
             if (j + jb < J0 + w) {
-                RLA_TRY(launch_trsm<T>(a, ld, j, jb, j + jb, J0 + w, d_info, st));
+                RLA_TRY(launch_trsm<T>(a, ld, j, jb, j + jb, J0 + w, d_info, s));
                 if (j + jb < n)
                     RLA_TRY(gemm_update<T>(size_t(n - j - jb), size_t(jb), size_t(J0 + w - j - jb),
                                            a + size_t(j + jb) * ld + j, ld, a + size_t(j) * ld + j + jb, ld,
-                                           a + size_t(j + jb) * ld + j + jb, ld, st));
+                                           a + size_t(j + jb) * ld + j + jb, ld, s));
             }
         }
+        return RLA_OK;
+    };
+    // A[J0+w:n, c0:c1) -= L21 * U12[:, c0:c1)   (k = w)
+    auto schur = [&](int J0, int w, int c0, int c1, cudaStream_t s) -> int {
+        if (c1 <= c0 || J0 + w >= n) return RLA_OK;
+        return gemm_update<T>(size_t(n - J0 - w), size_t(w), size_t(c1 - c0), a + size_t(J0 + w) * ld + J0, ld,
+                              a + size_t(J0) * ld + c0, ld, a + size_t(J0 + w) * ld + c0, ld, s);
+    };
+
+    // Look-ahead (depth 1): while the rank-256 Schur update of block k runs on the caller's stream over the
+    // columns right of block k+1, block k+1 -- whose columns were updated first -- is factored on a
+    // high-priority side stream.  The latency-bound panel kernels then overlap the tensor-pipe-bound update.
+    const bool lookahead = (g_lu_dbg & 4) == 0 && n > 2 * OUTER_W;
+    if (lookahead && ws.side == nullptr) {
+        int lo = 0, hi = 0;
+        RLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        RLA_CUDA(cudaStreamCreateWithPriority(&ws.side, cudaStreamNonBlocking, hi));
+        RLA_CUDA(cudaEventCreateWithFlags(&ws.ev_head, cudaEventDisableTiming));
+        RLA_CUDA(cudaEventCreateWithFlags(&ws.ev_fact, cudaEventDisableTiming));
+    }
+    RLA_TRY(factor_block(0, st));
+    for (int J0 = 0; J0 < n; J0 += OUTER_W) {
+        const int w = min(OUTER_W, n - J0);
         // interchanges of the whole outer block applied left and right of it (+ the row-origin vector)
         RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, plan, st));
-        if (J0 + w < n) {
-            // U12 = L11^-1 A12 by blocks of PW rows, then A22 -= L21 U12 (k = w)
-            for (int kb = 0; kb < w; kb += PW) {
-                const int jb = min(PW, w - kb);
-                RLA_TRY(launch_trsm<T>(a, ld, J0 + kb, jb, J0 + w, n, d_info, st));
-                if (kb + jb < w)
-                    RLA_TRY(gemm_update<T>(size_t(w - kb - jb), size_t(jb), size_t(n - J0 - w),
-                                           a + size_t(J0 + kb + jb) * ld + J0 + kb, ld,
-                                           a + size_t(J0 + kb) * ld + J0 + w, ld,
-                                           a + size_t(J0 + kb + jb) * ld + J0 + w, ld, st));
-            }
-            RLA_TRY(gemm_update<T>(size_t(n - J0 - w), size_t(w), size_t(n - J0 - w), a + size_t(J0 + w) * ld + J0, ld,
-                                   a + size_t(J0) * ld + J0 + w, ld, a + size_t(J0 + w) * ld + J0 + w, ld, st));
+        if (J0 + w >= n) break;
+        // U12 = L11^-1 A12 by blocks of PW rows
+        for (int kb = 0; kb < w; kb += PW) {
+            const int jb = min(PW, w - kb);
+            RLA_TRY(launch_trsm<T>(a, ld, J0 + kb, jb, J0 + w, n, d_info, st));
+            if (kb + jb < w)
+                RLA_TRY(gemm_update<T>(size_t(w - kb - jb), size_t(jb), size_t(n - J0 - w),
+                                       a + size_t(J0 + kb + jb) * ld + J0 + kb, ld,
+                                       a + size_t(J0 + kb) * ld + J0 + w, ld,
+                                       a + size_t(J0 + kb + jb) * ld + J0 + w, ld, st));
+        }
+        const int next = J0 + w;
+        const int wn = min(OUTER_W, n - next);
+        if (lookahead && next + wn < n) {
+            RLA_TRY(schur(J0, w, next, next + wn, st));                 // head: the next block's columns first
+            RLA_CUDA(cudaEventRecord(ws.ev_head, st));
+            RLA_CUDA(cudaStreamWaitEvent(ws.side, ws.ev_head, 0));
+            RLA_TRY(factor_block(next, ws.side));                       // || with the tail update below
+            RLA_CUDA(cudaEventRecord(ws.ev_fact, ws.side));
+            RLA_TRY(schur(J0, w, next + wn, n, st));                    // tail
+            RLA_CUDA(cudaStreamWaitEvent(st, ws.ev_fact, 0));
+        } else {
+            RLA_TRY(schur(J0, w, next, n, st));
+            RLA_TRY(factor_block(next, st));
         }
     }
     invert_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, d_perm, n, d_info);
