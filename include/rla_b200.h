@@ -125,6 +125,28 @@ RLA_API int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t 
 RLA_API int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm,
                    float *d_b, int32_t *d_info, void *stream);
 
+/* Building blocks of the 1D block-cyclic multi-GPU LU (driven by rulinalg_b200/sharded_lu.py, one
+ * process per GPU, panel broadcast over NCCL).  Local matrix: n rows x ncols_loc columns, row stride ld; the
+ * 256-wide global column block J of rank J mod g sits at local columns [(J/g)*256, ...).  Row indices are
+ * global.  d_plan is an opaque device buffer of rla_lu_plan_bytes() bytes holding a block's net row
+ * permutation; d_info must be zeroed by the caller before the first block.
+ *   factor_block : owner factors the block with diagonal at global row row0, stored at local column lcol0
+ *   laswp        : apply the block's interchanges to local columns [c0a,c1a) U [c0b,c1b)
+ *   update       : with the broadcast panel ((n-row0) x w, row stride ldp, L11 on top of L21) compute
+ *                  U12 = L11^-1 A12 and A22 -= L21 U12 on local columns [c0,c1)
+ *   rowid_*      : the row-origin vector every rank carries; perm_from_rowid gives PartialPivLu.p.perm */
+RLA_API size_t rla_lu_plan_bytes(void);
+RLA_API int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w,
+                             int32_t *d_info, void *d_plan, void *stream);
+RLA_API int rla_dlu_laswp_dev(double *a_loc, size_t ld, size_t w, const void *d_plan, const int32_t *d_info,
+                      size_t c0a, size_t c1a, size_t c0b, size_t c1b, void *stream);
+RLA_API int rla_dlu_update_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t w, const double *panel,
+                       size_t ldp, size_t c0, size_t c1, const int32_t *d_info, void *stream);
+RLA_API int rla_lu_rowid_init_dev(int32_t *rowid, size_t n, void *stream);
+RLA_API int rla_lu_rowid_apply_dev(const void *d_plan, int32_t *rowid, const int32_t *d_info, void *stream);
+RLA_API int rla_lu_perm_from_rowid_dev(const int32_t *rowid, int64_t *d_perm, size_t n, const int32_t *d_info,
+                               void *stream);
+
 /* Seeded U[lo, lo+scale) fill, bit-identical to the test oracle's generator, so that every
  * rank can synthesise its shard in HBM without a transfer.  Element (i,j) of the rows x cols
  * matrix uses counter offset + (row0+i)*cols_total + (col0+j). */

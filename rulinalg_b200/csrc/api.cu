@@ -455,6 +455,36 @@ int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
     return getrs_launch<float>(n, lu, ld, d_perm, d_b, static_cast<float *>(cx.dVec2.p), d_info,
                                static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
 }
+size_t rla_lu_plan_bytes(void) { return lu_plan_bytes(); }
+int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w, int32_t *d_info,
+                             void *d_plan, void *stream) {
+    RLA_TRY(ensure_ctx());
+    if (n > 0x3fffffffull || w == 0 || w > 256 || row0 + w > n) return RLA_ERR_INVALID;
+    return lu_factor_block_dev<double>(int(n), a_loc, ld, int(row0), int(lcol0), int(w), d_info, d_plan, tl_ctx.lu_ws,
+                                       pick_stream(stream));
+}
+int rla_dlu_laswp_dev(double *a_loc, size_t ld, size_t w, const void *d_plan, const int32_t *d_info, size_t c0a,
+                      size_t c1a, size_t c0b, size_t c1b, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return lu_laswp_dev<double>(a_loc, ld, int(w), d_plan, d_info, int(c0a), int(c1a), int(c0b), int(c1b), pick_stream(stream));
+}
+int rla_dlu_update_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t w, const double *panel, size_t ldp,
+                       size_t c0, size_t c1, const int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return lu_update_dev<double>(int(n), a_loc, ld, int(row0), int(w), panel, ldp, int(c0), int(c1), d_info, pick_stream(stream));
+}
+int rla_lu_rowid_init_dev(int32_t *rowid, size_t n, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return lu_rowid_init_dev(rowid, int(n), pick_stream(stream));
+}
+int rla_lu_rowid_apply_dev(const void *d_plan, int32_t *rowid, const int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return lu_rowid_apply_dev(d_plan, rowid, d_info, pick_stream(stream));
+}
+int rla_lu_perm_from_rowid_dev(const int32_t *rowid, int64_t *d_perm, size_t n, const int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return lu_perm_from_rowid_dev(rowid, d_perm, int(n), d_info, pick_stream(stream));
+}
 int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size_t ld, uint64_t seed, uint64_t offset,
                              double lo, double scale, void *stream) {
     RLA_TRY(ensure_ctx());

@@ -61,6 +61,20 @@ template <typename T>
 int getrs_launch(size_t n, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *d_tmp,
                  int32_t *d_info, int32_t *d_flags, cudaStream_t st);
 
+size_t lu_plan_bytes();
+template <typename T>
+int lu_factor_block_dev(int n, T *a_loc, size_t ld, int row0, int lcol0, int w, int32_t *d_info, void *d_plan,
+                        LuWorkspace &ws, cudaStream_t st);
+template <typename T>
+int lu_laswp_dev(T *a_loc, size_t ld, int w, const void *d_plan, const int32_t *d_info, int c0a, int c1a, int c0b,
+                 int c1b, cudaStream_t st);
+template <typename T>
+int lu_update_dev(int n, T *a_loc, size_t ld, int row0, int w, const T *panel, size_t ldp, int c0, int c1,
+                  const int32_t *d_info, cudaStream_t st);
+int lu_rowid_init_dev(int32_t *rowid, int n, cudaStream_t st);
+int lu_rowid_apply_dev(const void *d_plan, int32_t *rowid, const int32_t *d_info, cudaStream_t st);
+int lu_perm_from_rowid_dev(const int32_t *rowid, int64_t *perm, int n, const int32_t *d_info, cudaStream_t st);
+
 template <typename T>
 int fill_uniform_launch(T *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
                         uint64_t offset, T lo, T scale, cudaStream_t st);

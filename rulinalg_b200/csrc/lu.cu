@@ -261,20 +261,12 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                 }
                 if (lane == 0) sc.state->nf = nf;
             } else {
-                // outer block complete: publish the plan and permute the row-origin vector
+                // outer block complete: publish the plan (rowid_apply_kernel / laswp_apply_kernel consume it)
                 const int nt = w + nf;
-                int *ids = reinterpret_cast<int *>(panel_smem);
                 if (lane == 0) sc.plan->nt = nt;
                 for (int i = lane; i < nt; i += 32) {
-                    const int row = (i < w) ? J0 + i : st.fr[i - w];
-                    sc.plan->rows[i] = row;
+                    sc.plan->rows[i] = (i < w) ? J0 + i : st.fr[i - w];
                     sc.plan->origin[i] = (i < w) ? st.od[i] : st.of[i - w];
-                    ids[i] = sc.rowid[row];
-                }
-                __syncwarp();
-                for (int i = lane; i < nt; i += 32) {
-                    const int o = (i < w) ? st.od[i] : st.of[i - w];
-                    if (o != i) sc.rowid[(i < w) ? J0 + i : st.fr[i - w]] = ids[o];
                 }
             }
         }
@@ -472,25 +464,26 @@ constexpr int TRSM_COLS = TRSM_THREADS / 4;
 
 template <typename T>
 __global__ void __launch_bounds__(TRSM_THREADS)
-trsm_unit_lower_kernel(T *__restrict__ A, size_t ld, int j, int jb, int c0, int c1,
+trsm_unit_lower_kernel(const T *__restrict__ L, size_t ldl, int jb, T *__restrict__ B, size_t ldb, int ncols,
                        const int32_t *__restrict__ info) {
+    // L: jb x jb unit lower (top-left element), B: jb x ncols (top-left element); L and B may alias one matrix
     if (*info != 0) return;
     __shared__ T Ls[PW * (PW + 1)];
     const int tid = threadIdx.x;
     for (int idx = tid; idx < PW * PW; idx += TRSM_THREADS) {
         const int r = idx / PW, c = idx - r * PW;
-        Ls[r * (PW + 1) + c] = (r < jb && c < r) ? A[size_t(j + r) * ld + j + c] : T(0);
+        Ls[r * (PW + 1) + c] = (r < jb && c < r) ? L[size_t(r) * ldl + c] : T(0);
     }
     __syncthreads();
     const int lane = tid & 31;
     const int r = lane & 3;                                   // row residue owned by this thread
-    const int col = c0 + blockIdx.x * TRSM_COLS + (tid >> 5) * 8 + (lane >> 2);
-    const bool ok = col < c1;
+    const int col = blockIdx.x * TRSM_COLS + (tid >> 5) * 8 + (lane >> 2);
+    const bool ok = col < ncols;
     T x[PW / 4];
 #pragma unroll
     for (int ii = 0; ii < PW / 4; ++ii) {
         const int i = 4 * ii + r;
-        x[ii] = (ok && i < jb) ? A[size_t(j + i) * ld + col] : T(0);
+        x[ii] = (ok && i < jb) ? B[size_t(i) * ldb + col] : T(0);
     }
     const T *Lr = Ls + r * (PW + 1);
 #pragma unroll
@@ -504,7 +497,21 @@ trsm_unit_lower_kernel(T *__restrict__ A, size_t ld, int j, int jb, int c0, int 
 #pragma unroll
     for (int ii = 0; ii < PW / 4; ++ii) {
         const int i = 4 * ii + r;
-        if (ok && i >= 1 && i < jb) A[size_t(j + i) * ld + col] = x[ii];
+        if (ok && i >= 1 && i < jb) B[size_t(i) * ldb + col] = x[ii];
+    }
+}
+
+// rowid <- plan applied to it (the row-origin vector from which `perm` is produced)
+__global__ void __launch_bounds__(256)
+rowid_apply_kernel(const LaswpPlan *__restrict__ plan, int32_t *__restrict__ rowid, const int32_t *__restrict__ info) {
+    if (*info != 0) return;
+    __shared__ int ids[2 * LASWP_MAXJB];
+    const int nt = plan->nt;
+    for (int i = threadIdx.x; i < nt; i += 256) ids[i] = rowid[plan->rows[i]];
+    __syncthreads();
+    for (int i = threadIdx.x; i < nt; i += 256) {
+        const int o = plan->origin[i];
+        if (o != i) rowid[plan->rows[i]] = ids[o];
     }
 }
 
@@ -535,33 +542,8 @@ int gemm_update<float>(size_t m, size_t k, size_t n, const float *a, size_t lda,
 }
 
 int g_num_sms = 0;
-
-template <typename T>
-int launch_laswp(T *a, size_t ld, int J, int jb, const int32_t *ipiv, const int32_t *info, int c0a, int c1a,
-                 int c0b, int c1b, LaswpPlan *plan, cudaStream_t st) {
-    (void)J; (void)ipiv;
-    const int ncols = (c1a - c0a) + (c1b - c0b);
-    if (ncols <= 0) return RLA_OK;
-    const size_t smem = size_t(2) * jb * LASWP_CW * sizeof(T);
-    static bool attr = false;
-    if (!attr) {
-        RLA_CUDA(cudaFuncSetAttribute(laswp_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LASWP_MAXJB * LASWP_CW * 8));
-        attr = true;
-    }
-    const int blocks = (ncols + LASWP_CW - 1) / LASWP_CW;
-    laswp_apply_kernel<T><<<blocks, LASWP_THREADS, smem, st>>>(a, ld, plan, info, c0a, c1a, c0b, c1b);
-    RLA_LAUNCHED();
-    return RLA_OK;
-}
-
-template <typename T>
-int launch_trsm(T *a, size_t ld, int j, int jb, int c0, int c1, const int32_t *info, cudaStream_t st) {
-    if (c1 <= c0 || jb <= 1) return RLA_OK;
-    const int blocks = (c1 - c0 + TRSM_COLS - 1) / TRSM_COLS;
-    trsm_unit_lower_kernel<T><<<blocks, TRSM_THREADS, 0, st>>>(a, ld, j, jb, c0, c1, info);
-    RLA_LAUNCHED();
-    return RLA_OK;
-}
+int g_lu_gmax_ref();
+int g_lu_dbg_ref();
 
 // scratch layout (bytes): packets | rowbuf | diagbuf | result | laswp plan | plan state
 constexpr size_t SC_PACKETS = 0;
@@ -572,24 +554,13 @@ constexpr size_t SC_PLAN = SC_RESULT + 256;
 constexpr size_t SC_STATE = SC_PLAN + ((sizeof(LaswpPlan) + 255) / 256) * 256;
 constexpr size_t SC_TOTAL = SC_STATE + sizeof(PlanState) + 256;
 
-}  // namespace
-
-int g_lu_gmax = 1 << 30;      // rla_set_tuning("lu_gmax", v): cap on the number of row CTAs of the panel kernel
-int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): timing experiments only (bit0: hub skips the row swaps)
-
-template <typename T>
-int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
-    if (n_ > 0x7fffffffull / 2) return RLA_ERR_INVALID;
-    const int n = int(n_);
-    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
-    if (n == 0) return RLA_OK;
+int ensure_workspace(LuWorkspace &ws, int n, cudaStream_t st) {
     if (g_num_sms == 0) {
         int dev = 0;
         RLA_CUDA(cudaGetDevice(&dev));
         RLA_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
     }
-    // workspace: ipiv[n] + rowid[n] (int32) and the panel scratch
-    if (ws.ipiv_cap < size_t(2) * n) {
+    if (ws.ipiv_cap < size_t(2) * n) {                 // ipiv[n] + rowid[n]
         if (ws.ipiv) RLA_CUDA(cudaFree(ws.ipiv));
         ws.ipiv = nullptr;
         ws.ipiv_cap = 0;
@@ -605,67 +576,132 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         ws.tag = 0;
         RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
     }
-    int32_t *ipiv = ws.ipiv;
-    int32_t *rowid = ws.ipiv + n;
+    // tags are unique per (launch, column) for the lifetime of the scratch buffer; re-zero before wrap-around
+    if (ws.tag > 0xffffffffu - 2u * unsigned(n) - 16u) {
+        RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
+        ws.tag = 0;
+    }
+    return RLA_OK;
+}
+
+PanelScratch scratch_view(LuWorkspace &ws) {
     unsigned char *sp = static_cast<unsigned char *>(ws.scratch);
     PanelScratch sc;
     sc.packets = reinterpret_cast<Msg *>(sp + SC_PACKETS);
     sc.rowbuf = reinterpret_cast<Msg *>(sp + SC_ROWBUF);
     sc.diagbuf = reinterpret_cast<Msg *>(sp + SC_DIAGBUF);
     sc.result = reinterpret_cast<Msg *>(sp + SC_RESULT);
-    LaswpPlan *plan = reinterpret_cast<LaswpPlan *>(sp + SC_PLAN);
-    sc.plan = plan;
+    sc.plan = reinterpret_cast<LaswpPlan *>(sp + SC_PLAN);
     sc.state = reinterpret_cast<PlanState *>(sp + SC_STATE);
-    sc.rowid = rowid;
-    // tags are unique per (launch, column) for the lifetime of the scratch buffer; re-zero before wrap-around
-    if (ws.tag > 0xffffffffu - 2u * unsigned(n) - 16u) {
-        RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
-        ws.tag = 0;
-    }
-    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, n);
-    RLA_LAUNCHED();
+    sc.rowid = nullptr;
+    return sc;
+}
 
+// Factor the outer block whose diagonal starts at (J0, J0) of `a` (w <= 256 columns, rows J0..n-1).
+// `a` may be a shifted base pointer so that "column J0" is wherever the block lives in a local matrix
+// (distributed layout); only columns [J0, J0+w) are touched.  The block's net permutation goes to *plan.
+template <typename T>
+int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t *ipiv, int32_t *d_info,
+                 LaswpPlan *plan, cudaStream_t s) {
     static bool attr = false;
     if (!attr) {
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
-    // factor the 256-column outer block at J0 (its columns must already carry every earlier Schur update)
-    auto factor_block = [&](int J0, cudaStream_t s) -> int {
-        const int w = min(OUTER_W, n - J0);
-        for (int j = J0; j < J0 + w; j += PW) {
-            const int jb = min(PW, J0 + w - j);
-            const int nrem = n - j;
-            int G = min(min(min(g_num_sms - 1, HUB_ROOT_THREADS), g_lu_gmax), max(1, (nrem + 63) / 64));
-            while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
-            int R = (nrem + G - 1) / G;
-            size_t smem = size_t(R) * PLDS * sizeof(T);
-            if (smem < 2 * LASWP_MAXJB * sizeof(int)) smem = 2 * LASWP_MAXJB * sizeof(int);   // hub's id scratch
-            if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
-            {
-                // +1 hub CTA: reduces the candidates, applies the interchanges to the rest of the outer block and
-                // builds the outer block's net permutation plan (consumed by laswp_apply_kernel) on the fly
-                const int grid = G + 1;
-                T *a_ = a;
-                size_t ld_ = ld;
-                int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G, J0_ = J0, w_ = w, dbg_ = g_lu_dbg;
-                unsigned tag_base = ws.tag;
-                void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base, &J0_, &w_, &dbg_};
-                RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, s));
-                note_launch();
-                ws.tag += unsigned(jb);
-            }
-            // U12 and the Schur update inside the outer block
-            if (j + jb < J0 + w) {
-                RLA_TRY(launch_trsm<T>(a, ld, j, jb, j + jb, J0 + w, d_info, s));
-                if (j + jb < n)
-                    RLA_TRY(gemm_update<T>(size_t(n - j - jb), size_t(jb), size_t(J0 + w - j - jb),
-                                           a + size_t(j + jb) * ld + j, ld, a + size_t(j) * ld + j + jb, ld,
-                                           a + size_t(j + jb) * ld + j + jb, ld, s));
-            }
+    PanelScratch sc = scratch_view(ws);
+    sc.plan = plan;
+    for (int j = J0; j < J0 + w; j += PW) {
+        const int jb = min(PW, J0 + w - j);
+        const int nrem = n - j;
+        int G = min(min(min(g_num_sms - 1, HUB_ROOT_THREADS), g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
+        while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
+        int R = (nrem + G - 1) / G;
+        size_t smem = size_t(R) * PLDS * sizeof(T);
+        if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
+        {
+            // +1 hub CTA: reduces the candidates, applies the interchanges to the rest of the outer block and
+            // builds the outer block's net permutation plan on the fly
+            const int grid = G + 1;
+            T *a_ = a;
+            size_t ld_ = ld;
+            int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G, J0_ = J0, w_ = w, dbg_ = g_lu_dbg_ref();
+            unsigned tag_base = ws.tag;
+            void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base, &J0_, &w_, &dbg_};
+            RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, s));
+            note_launch();
+            ws.tag += unsigned(jb);
         }
-        return RLA_OK;
-    };
+        // U12 and the Schur update inside the outer block
+        if (j + jb < J0 + w) {
+            const int nc = J0 + w - j - jb;
+            trsm_unit_lower_kernel<T><<<(nc + TRSM_COLS - 1) / TRSM_COLS, TRSM_THREADS, 0, s>>>(
+                a + size_t(j) * ld + j, ld, jb, a + size_t(j) * ld + j + jb, ld, nc, d_info);
+            RLA_LAUNCHED();
+            if (j + jb < n)
+                RLA_TRY(gemm_update<T>(size_t(n - j - jb), size_t(jb), size_t(nc), a + size_t(j + jb) * ld + j, ld,
+                                       a + size_t(j) * ld + j + jb, ld, a + size_t(j + jb) * ld + j + jb, ld, s));
+        }
+    }
+    return RLA_OK;
+}
+
+// Apply a block's net permutation to columns [c0a,c1a) U [c0b,c1b) of `a`.
+template <typename T>
+int apply_laswp(T *a, size_t ld, int w, const LaswpPlan *plan, const int32_t *info, int c0a, int c1a, int c0b, int c1b,
+                cudaStream_t st) {
+    const int ncols = (c1a - c0a) + (c1b - c0b);
+    if (ncols <= 0) return RLA_OK;
+    const size_t smem = size_t(2) * w * LASWP_CW * sizeof(T);
+    static bool attr = false;
+    if (!attr) {
+        RLA_CUDA(cudaFuncSetAttribute(laswp_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LASWP_MAXJB * LASWP_CW * 8));
+        attr = true;
+    }
+    const int blocks = (ncols + LASWP_CW - 1) / LASWP_CW;
+    laswp_apply_kernel<T><<<blocks, LASWP_THREADS, smem, st>>>(a, ld, plan, info, c0a, c1a, c0b, c1b);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+// U12 = L11^-1 B by blocks of PW rows (L11: w x w unit lower at L, B: w x ncols), all in place.
+template <typename T>
+int trsm_block(const T *L, size_t ldl, int w, T *B, size_t ldb, int ncols, const int32_t *info, cudaStream_t st) {
+    if (ncols <= 0) return RLA_OK;
+    for (int kb = 0; kb < w; kb += PW) {
+        const int jb = min(PW, w - kb);
+        if (jb > 1) {
+            trsm_unit_lower_kernel<T><<<(ncols + TRSM_COLS - 1) / TRSM_COLS, TRSM_THREADS, 0, st>>>(
+                L + size_t(kb) * ldl + kb, ldl, jb, B + size_t(kb) * ldb, ldb, ncols, info);
+            RLA_LAUNCHED();
+        }
+        if (kb + jb < w)
+            RLA_TRY(gemm_update<T>(size_t(w - kb - jb), size_t(jb), size_t(ncols), L + size_t(kb + jb) * ldl + kb, ldl,
+                                   B + size_t(kb) * ldb, ldb, B + size_t(kb + jb) * ldb, ldb, st));
+    }
+    return RLA_OK;
+}
+
+}  // namespace
+
+int g_lu_gmax = 1 << 30;      // rla_set_tuning("lu_gmax", v): cap on the number of row CTAs of the panel kernel
+int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bit0: hub skips row swaps, bit2: no look-ahead)
+namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } }
+
+size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
+
+template <typename T>
+int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
+    if (n_ > 0x7fffffffull / 2) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    if (n == 0) return RLA_OK;
+    RLA_TRY(ensure_workspace(ws, n, st));
+    int32_t *ipiv = ws.ipiv;
+    int32_t *rowid = ws.ipiv + n;
+    LaswpPlan *plan = scratch_view(ws).plan;
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, n);
+    RLA_LAUNCHED();
+
     // A[J0+w:n, c0:c1) -= L21 * U12[:, c0:c1)   (k = w)
     auto schur = [&](int J0, int w, int c0, int c1, cudaStream_t s) -> int {
         if (c1 <= c0 || J0 + w >= n) return RLA_OK;
@@ -684,35 +720,28 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         RLA_CUDA(cudaEventCreateWithFlags(&ws.ev_head, cudaEventDisableTiming));
         RLA_CUDA(cudaEventCreateWithFlags(&ws.ev_fact, cudaEventDisableTiming));
     }
-    RLA_TRY(factor_block(0, st));
+    RLA_TRY(factor_block<T>(ws, a, ld, n, 0, min(OUTER_W, n), ipiv, d_info, plan, st));
     for (int J0 = 0; J0 < n; J0 += OUTER_W) {
         const int w = min(OUTER_W, n - J0);
-        // interchanges of the whole outer block applied left and right of it (+ the row-origin vector)
-        RLA_TRY(launch_laswp<T>(a, ld, J0, w, ipiv, d_info, 0, J0, J0 + w, n, plan, st));
+        // interchanges of the whole outer block applied left and right of it, and to the row-origin vector
+        rowid_apply_kernel<<<1, 256, 0, st>>>(plan, rowid, d_info);
+        RLA_LAUNCHED();
+        RLA_TRY(apply_laswp<T>(a, ld, w, plan, d_info, 0, J0, J0 + w, n, st));
         if (J0 + w >= n) break;
-        // U12 = L11^-1 A12 by blocks of PW rows
-        for (int kb = 0; kb < w; kb += PW) {
-            const int jb = min(PW, w - kb);
-            RLA_TRY(launch_trsm<T>(a, ld, J0 + kb, jb, J0 + w, n, d_info, st));
-            if (kb + jb < w)
-                RLA_TRY(gemm_update<T>(size_t(w - kb - jb), size_t(jb), size_t(n - J0 - w),
-                                       a + size_t(J0 + kb + jb) * ld + J0 + kb, ld,
-                                       a + size_t(J0 + kb) * ld + J0 + w, ld,
-                                       a + size_t(J0 + kb + jb) * ld + J0 + w, ld, st));
-        }
+        RLA_TRY(trsm_block<T>(a + size_t(J0) * ld + J0, ld, w, a + size_t(J0) * ld + J0 + w, ld, n - J0 - w, d_info, st));
         const int next = J0 + w;
         const int wn = min(OUTER_W, n - next);
         if (lookahead && next + wn < n) {
             RLA_TRY(schur(J0, w, next, next + wn, st));                 // head: the next block's columns first
             RLA_CUDA(cudaEventRecord(ws.ev_head, st));
             RLA_CUDA(cudaStreamWaitEvent(ws.side, ws.ev_head, 0));
-            RLA_TRY(factor_block(next, ws.side));                       // || with the tail update below
+            RLA_TRY(factor_block<T>(ws, a, ld, n, next, wn, ipiv, d_info, plan, ws.side));   // || with the tail update
             RLA_CUDA(cudaEventRecord(ws.ev_fact, ws.side));
             RLA_TRY(schur(J0, w, next + wn, n, st));                    // tail
             RLA_CUDA(cudaStreamWaitEvent(st, ws.ev_fact, 0));
         } else {
             RLA_TRY(schur(J0, w, next, n, st));
-            RLA_TRY(factor_block(next, st));
+            RLA_TRY(factor_block<T>(ws, a, ld, n, next, wn, ipiv, d_info, plan, st));
         }
     }
     invert_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, d_perm, n, d_info);
@@ -722,5 +751,57 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
 
 template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
 template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
+
+// ---------------------------------------------------------------------------------------------
+// Building blocks of the 1D block-cyclic multi-GPU LU (rulinalg_b200/sharded_lu.py drives them).
+// Local matrix: n rows x ncols_loc columns (row stride ld); global column block J (256 wide) of rank
+// J mod g sits at local columns [(J/g)*256, ...).  All row indices are global.
+// ---------------------------------------------------------------------------------------------
+// Owner: factor the block whose global diagonal starts at row0 and whose columns sit at local column lcol0.
+template <typename T>
+int lu_factor_block_dev(int n, T *a_loc, size_t ld, int row0, int lcol0, int w, int32_t *d_info, void *d_plan,
+                        LuWorkspace &ws, cudaStream_t st) {
+    RLA_TRY(ensure_workspace(ws, n, st));
+    T *shifted = a_loc + lcol0 - row0;      // "column row0" of `shifted` is local column lcol0
+    return factor_block<T>(ws, shifted, ld, n, row0, w, ws.ipiv, d_info, static_cast<LaswpPlan *>(d_plan), st);
+}
+// Everyone: apply the block's interchanges to local columns [c0a,c1a) U [c0b,c1b).
+template <typename T>
+int lu_laswp_dev(T *a_loc, size_t ld, int w, const void *d_plan, const int32_t *d_info, int c0a, int c1a, int c0b,
+                 int c1b, cudaStream_t st) {
+    return apply_laswp<T>(a_loc, ld, w, static_cast<const LaswpPlan *>(d_plan), d_info, c0a, c1a, c0b, c1b, st);
+}
+// Everyone: with the broadcast panel P ((n-row0) x w, row stride ldp; L11 on top of L21), update local columns
+// [c0,c1): U12 = L11^-1 A12, then A22 -= L21 U12.
+template <typename T>
+int lu_update_dev(int n, T *a_loc, size_t ld, int row0, int w, const T *panel, size_t ldp, int c0, int c1,
+                  const int32_t *d_info, cudaStream_t st) {
+    if (c1 <= c0) return RLA_OK;
+    RLA_TRY(trsm_block<T>(panel, ldp, w, a_loc + size_t(row0) * ld + c0, ld, c1 - c0, d_info, st));
+    if (row0 + w < n)
+        RLA_TRY(gemm_update<T>(size_t(n - row0 - w), size_t(w), size_t(c1 - c0), panel + size_t(w) * ldp, ldp,
+                               a_loc + size_t(row0) * ld + c0, ld, a_loc + size_t(row0 + w) * ld + c0, ld, st));
+    return RLA_OK;
+}
+int lu_rowid_init_dev(int32_t *rowid, int n, cudaStream_t st) {
+    if (n <= 0) return RLA_OK;
+    iota_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, n);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+int lu_rowid_apply_dev(const void *d_plan, int32_t *rowid, const int32_t *d_info, cudaStream_t st) {
+    rowid_apply_kernel<<<1, 256, 0, st>>>(static_cast<const LaswpPlan *>(d_plan), rowid, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+int lu_perm_from_rowid_dev(const int32_t *rowid, int64_t *perm, int n, const int32_t *d_info, cudaStream_t st) {
+    if (n <= 0) return RLA_OK;
+    invert_perm_kernel<<<(n + 255) / 256, 256, 0, st>>>(rowid, perm, n, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+template int lu_factor_block_dev<double>(int, double *, size_t, int, int, int, int32_t *, void *, LuWorkspace &, cudaStream_t);
+template int lu_laswp_dev<double>(double *, size_t, int, const void *, const int32_t *, int, int, int, int, cudaStream_t);
+template int lu_update_dev<double>(int, double *, size_t, int, int, const double *, size_t, int, int, const int32_t *, cudaStream_t);
 
 }  // namespace rla

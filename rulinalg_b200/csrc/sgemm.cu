@@ -129,14 +129,6 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     for (int kt = 0; kt < KT; ++kt) {
         cp_async_wait<STAGES - 2>();
         __syncthreads();
-        {
-            const int nk = kt + STAGES - 1;
-            if (nk < KT) {
-                const int s = nk % STAGES;
-                load_slab<ALIGNED>(As + s * A_STAGE, Bs + s * B_STAGE, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
-            }
-            cp_async_commit();
-        }
         const int s = kt % STAGES;
         const float *ap = As + s * A_STAGE + (ty * 4) * LDAS;
         const float *bp = Bs + s * B_STAGE + tx * 4;
@@ -153,13 +145,25 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
                 const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(bp + (kk + q) * LDBS);
                 const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(bp + (kk + q) * LDBS + 64);
                 const unsigned long long bv[4] = {b0.x, b0.y, b1.x, b1.y};
+                // j outer / i inner: the 64-bit B pair stays in the operand-reuse cache across the 8 rows, so each
+                // FFMA2 fetches one scalar (A) and one pair (accumulator) from the register file
 #pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const float av = (q == 0) ? a4[i].x : (q == 1) ? a4[i].y : (q == 2) ? a4[i].z : a4[i].w;
-                    const unsigned long long a2 = pack2(av, av);     // ptxas folds this into the .F32 broadcast operand
+                for (int j = 0; j < 4; ++j) {
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) ffma2(acc[i][j], a2, bv[j]);
+                    for (int i = 0; i < 8; ++i) {
+                        const float av = (q == 0) ? a4[i].x : (q == 1) ? a4[i].y : (q == 2) ? a4[i].z : a4[i].w;
+                        ffma2(acc[i][j], pack2(av, av), bv[j]);   // ptxas folds the pack into the .F32 broadcast operand
+                    }
                 }
+            }
+            if (kk == 0) {
+                // queue the copies for slab kt+STAGES-1 once the FMA pipe has work (same idea as dgemm.cu)
+                const int nk = kt + STAGES - 1;
+                if (nk < KT) {
+                    const int ns = nk % STAGES;
+                    load_slab<ALIGNED>(As + ns * A_STAGE, Bs + ns * B_STAGE, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
+                }
+                cp_async_commit();
             }
         }
     }
