@@ -16,6 +16,7 @@ namespace rla {
 
 extern int g_dgemm_cfg;   // dgemm.cu
 extern int g_lu_gmax, g_lu_dbg;   // lu.cu
+int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 
 namespace {
 
@@ -190,10 +191,52 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
     RLA_TRY(cx.dC.ensure(m * ldc * sizeof(T)));
     T *dA = static_cast<T *>(cx.dA.p), *dB = static_cast<T *>(cx.dB.p), *dC = static_cast<T *>(cx.dC.p);
 
+    const size_t bytes_per_row = (k + n) * sizeof(T);
+    const bool big = m * bytes_per_row > (size_t(96) << 20);
+    if (big && beta == T(0) && k > 0 && m >= 1024 && n >= 1024 && g_host_gemm_2d) {
+        // 2-D wavefront pipeline.  A is cut into S row panels, B into S column chunks; step s uploads panel s
+        // and chunk s, then computes every C tile that just became computable (row strip s x [0..s], column strip
+        // [0..s-1] x s) and downloads it.  Work availability grows quadratically while uploads proceed linearly,
+        // so the kernel starts after 2/S of the H2D traffic instead of after all of B, and PCIe in both
+        // directions stays busy under the DMMA kernel.
+        const size_t S = 8;
+        const size_t pm = ((m + S - 1) / S + 127) / 128 * 128, pn = ((n + S - 1) / S + 127) / 128 * 128;
+        const size_t sm = (m + pm - 1) / pm, sn = (n + pn - 1) / pn;
+        const size_t steps = sm > sn ? sm : sn;
+        while (cx.events.size() < 2 * steps + 1) {
+            cudaEvent_t e;
+            RLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            cx.events.push_back(e);
+        }
+        for (size_t st = 0; st < steps; ++st) {
+            const size_t r0 = st * pm, c0 = st * pn;
+            const size_t rows = st < sm ? (r0 + pm <= m ? pm : m - r0) : 0;
+            const size_t cols = st < sn ? (c0 + pn <= n ? pn : n - c0) : 0;
+            if (rows) RLA_TRY(upload_matrix(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, cx.copy_in));
+            if (cols) RLA_TRY(upload_matrix(dB + c0, ldb, hb + c0, hrsb, k, cols, cx.copy_in));
+            RLA_CUDA(cudaEventRecord(cx.events[2 * st], cx.copy_in));
+            RLA_CUDA(cudaStreamWaitEvent(cx.stream, cx.events[2 * st], 0));
+            // row strip: rows of panel st against every chunk uploaded so far (including this step's)
+            const size_t ncols_avail = (st + 1 < sn ? (st + 1) * pn : n);
+            // column strip: panels before st against this step's chunk
+            const size_t nrows_prev = (st < sm ? st * pm : m);
+            // launch the larger strip first so its download overlaps the smaller strip's kernel
+            if (rows) RLA_TRY(gemm_dev<T>(rows, k, ncols_avail, alpha, dA + r0 * lda, lda, dB, ldb, beta, dC + r0 * ldc, ldc, cx.stream));
+            RLA_CUDA(cudaEventRecord(cx.events[2 * st + 1], cx.stream));
+            RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * st + 1], 0));
+            if (rows) RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, ncols_avail, cx.copy_out));
+            if (cols && nrows_prev) {
+                RLA_TRY(gemm_dev<T>(nrows_prev, k, cols, alpha, dA, lda, dB + c0, ldb, beta, dC + c0, ldc, cx.stream));
+                // reuse the input event slot of this step for the second strip's completion
+                RLA_CUDA(cudaEventRecord(cx.events[2 * st], cx.stream));
+                RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * st], 0));
+                RLA_TRY(download_matrix(hc + c0, hrsc, dC + c0, ldc, nrows_prev, cols, cx.copy_out));
+            }
+        }
+    } else {
     // row-panel pipeline: panel height chosen so that a panel is >= ~32 MiB of A+C traffic
     size_t panel = m;
-    const size_t bytes_per_row = (k + n) * sizeof(T);
-    if (m * bytes_per_row > (size_t(96) << 20)) {
+    if (big) {
         panel = ((size_t(32) << 20) / bytes_per_row + 127) / 128 * 128;
         if (panel < 128) panel = 128;
         if (panel > m) panel = m;
@@ -215,6 +258,7 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         RLA_CUDA(cudaEventRecord(cx.events[2 * p + 1], cx.stream));
         RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * p + 1], 0));
         RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, n, cx.copy_out));
+    }
     }
     RLA_CUDA(cudaStreamSynchronize(cx.copy_out));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
@@ -506,6 +550,10 @@ int rla_set_tuning(const char *key, int value) {
     if (strcmp(key, "lu_gmax") == 0) {
         if (value < 1) return RLA_ERR_INVALID;
         g_lu_gmax = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "host_gemm_2d") == 0) {
+        g_host_gemm_2d = value ? 1 : 0;
         return RLA_OK;
     }
     if (strcmp(key, "lu_dbg") == 0) {

@@ -28,7 +28,9 @@ constexpr int BAND = 16;
 
 // two independent IEEE fp32 FMAs: c.{x,y} = a.{x,y} * b.{x,y} + c.{x,y}
 __device__ __forceinline__ void ffma2(unsigned long long &c, unsigned long long a, unsigned long long b) {
-    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    // volatile: keeps the j-outer / i-inner issue order below, so the 64-bit B pair sits in the operand
+    // reuse cache for 8 consecutive FFMA2 and the register file only supplies the accumulator pair + A scalar
+    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
 }
 __device__ __forceinline__ unsigned long long pack2(float x, float y) {
     unsigned long long r;

@@ -190,6 +190,24 @@ def test_gemm_device_twin_odd_ld(rla, oracle, dtype):
     assert np.max(np.abs(got - ref)) <= 4 * gamma(k + 1, dtype) * (k + 1)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_gemm_host_2d_wavefront_pipeline(rla, oracle, dtype):
+    # large host-pointer products take the 2-D wavefront H2D/kernel/D2H pipeline (ragged panels and chunks here);
+    # it must agree bit-for-bit with the row-panel pipeline (same per-element arithmetic) and with the oracle
+    m, k, n = (3000, 3100, 2500) if dtype == np.float64 else (4000, 4100, 3500)
+    a = oracle.fill_uniform((m, k), 12, dtype)
+    b = oracle.fill_uniform((k, n), 2049, dtype)
+    l = rla.lib()
+    assert l.rla_set_tuning(b"host_gemm_2d", 1) == 0
+    got2d = gpu_gemm_host(rla, a, b)
+    assert l.rla_set_tuning(b"host_gemm_2d", 0) == 0
+    got1d = gpu_gemm_host(rla, a, b)
+    assert l.rla_set_tuning(b"host_gemm_2d", 1) == 0
+    assert not np.isnan(got2d).any()
+    assert np.array_equal(got2d, got1d)
+    check_gemm(oracle, a, b, got2d, positive=True)
+
+
 def test_gemm_degenerate(rla):
     # m*n == 0 -> no-op; k == 0 with beta == 0 -> zero fill
     assert (rla.Matrix.zeros(0, 3) * rla.Matrix.zeros(3, 4)).rows() == 0
