@@ -5,32 +5,33 @@
 // Design (DESIGN.md "K2"):
 //   CTA tile 128x128, k-slab 16, 256 threads, 8x8 register tile per thread laid out as 2x2 blocks
 //   of 4x4 (rows ty*4+{0..3}, 64+ty*4+{0..3}; cols tx*4.., 64+tx*4..) so shared reads are LDS.128
-//   and C stores are 256 contiguous bytes per half-row.  A and B slabs go global->shared with
-//   16-byte cp.async in a 3-stage ring, A kept in its native [m][k] orientation (row padded to
-//   20 floats so the two row groups of a warp land in different bank quads), B as [k][n].
+//   and C stores are 256 contiguous bytes per half-row.  Two CTAs per SM (<= 128 registers).
 //   The 8x8 tile is held as 32 packed float2 accumulators (pairs along n) and updated with the
-//   Blackwell packed FP32 FMA  fma.rn.f32x2 (SASS FFMA2, scalar-broadcast A operand): two IEEE
-//   binary32 FMAs per lane per instruction, which halves the issue-slot and register-port pressure
-//   that capped the scalar-FFMA version at 58 % of the FMA pipe (ncu: dispatch stalls).  Per 4
-//   k-steps a thread issues 8+8 LDS.128 for 128 FFMA2.  Two CTAs per SM (<=128 registers).
+//   Blackwell packed FP32 FMA  fma.rn.f32x2 (SASS FFMA2, scalar-broadcast A operand that ptxas folds
+//   from mov.b64 {x,x}): two IEEE binary32 FMAs per lane per instruction, halving issue-slot and
+//   register-port pressure (the scalar-FFMA version sat at 58 % of the FMA pipe with 1.2 dispatch-stall
+//   cycles per issue).
+//   A is stored k-major in shared memory (As[k][m], transposed on the way in: LDG.128 along k -> 4
+//   STS.32) so one k-step needs only 2+2 LDS.128 = 16 fragment registers; that leaves room to
+//   DOUBLE-BUFFER the fragments (load k+1 while the FFMA2s of k issue) inside the 128-register budget.
+//   The first FFMA2 version kept A as [m][k] float4 fragments (32 live registers, no double buffering):
+//   every warp alternated LDS bursts and FFMA2 bursts and the FMA pipe idled 31 % of the time.
+//   Global loads for slab kt+1 are issued before slab kt's math and parked in registers (A) / cp.async (B).
 #include "common.cuh"
 
 namespace rla {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, STAGES = 3, THREADS = 256;
-constexpr int LDAS = BK + 4;   // floats
-constexpr int LDBS = BN + 4;
-constexpr int A_STAGE = BM * LDAS;
-constexpr int B_STAGE = BK * LDBS;
-constexpr size_t SMEM_BYTES = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(float);
+constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256;
+constexpr int LDT = BM + 4;    // padded row of the k-major A tile and of the B tile (floats)
+constexpr int TILE = BK * LDT; // floats per operand per stage
+constexpr int STAGES = 2;
+constexpr size_t SMEM_BYTES = size_t(STAGES) * 2 * TILE * sizeof(float);
 constexpr int BAND = 16;
 
 // two independent IEEE fp32 FMAs: c.{x,y} = a.{x,y} * b.{x,y} + c.{x,y}
 __device__ __forceinline__ void ffma2(unsigned long long &c, unsigned long long a, unsigned long long b) {
-    // volatile: keeps the j-outer / i-inner issue order below, so the 64-bit B pair sits in the operand
-    // reuse cache for 8 consecutive FFMA2 and the register file only supplies the accumulator pair + A scalar
-    asm volatile("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
+    asm("fma.rn.f32x2 %0, %1, %2, %0;" : "+l"(c) : "l"(a), "l"(b));
 }
 __device__ __forceinline__ unsigned long long pack2(float x, float y) {
     unsigned long long r;
@@ -43,54 +44,24 @@ __device__ __forceinline__ float2 unpack2(unsigned long long v) {
     return r;
 }
 
-template <bool ALIGNED>
-__device__ __forceinline__ void load_slab(float *As, float *Bs, const float *__restrict__ A, size_t lda,
-                                          const float *__restrict__ B, size_t ldb, int M, int N, int K,
-                                          int m0, int n0, int k0, int tid) {
-    if (ALIGNED) {
-        const int ca = tid & 3, ra = tid >> 2;
+struct Frag {
+    float4 a0, a1;            // A[k][ty*4..+3], A[k][64+ty*4..+3]
+    ulonglong2 b0, b1;        // B[k][tx*4..+3] as two float2 pairs, B[k][64+tx*4..+3]
+};
+__device__ __forceinline__ void load_frag(Frag &f, const float *ap, const float *bp, int kk) {
+    f.a0 = *reinterpret_cast<const float4 *>(ap + kk * LDT);
+    f.a1 = *reinterpret_cast<const float4 *>(ap + kk * LDT + 64);
+    f.b0 = *reinterpret_cast<const ulonglong2 *>(bp + kk * LDT);
+    f.b1 = *reinterpret_cast<const ulonglong2 *>(bp + kk * LDT + 64);
+}
+__device__ __forceinline__ void mma_frag(unsigned long long (&acc)[8][4], const Frag &f) {
+    const float av[8] = {f.a0.x, f.a0.y, f.a0.z, f.a0.w, f.a1.x, f.a1.y, f.a1.z, f.a1.w};
+    const unsigned long long bv[4] = {f.b0.x, f.b0.y, f.b1.x, f.b1.y};
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int row = ra + 64 * i;
-            const int gk = k0 + 4 * ca;
-            int bytes = 0;
-            const float *src = A;
-            if (m0 + row < M && gk < K) {
-                bytes = min(K - gk, 4) * 4;
-                src = A + size_t(m0 + row) * lda + gk;
-            }
-            cp_async16(smem_u32(As + row * LDAS + 4 * ca), src, bytes);
-        }
-        const int cb = tid & 31, rb = tid >> 5;
+    for (int i = 0; i < 8; ++i) {
+        const unsigned long long a2 = pack2(av[i], av[i]);
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int row = rb + 8 * i;
-            const int gn = n0 + 4 * cb;
-            int bytes = 0;
-            const float *src = B;
-            if (k0 + row < K && gn < N) {
-                bytes = min(N - gn, 4) * 4;
-                src = B + size_t(k0 + row) * ldb + gn;
-            }
-            cp_async16(smem_u32(Bs + row * LDBS + 4 * cb), src, bytes);
-        }
-    } else {
-        const int ca = tid & 15, ra = tid >> 4;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = ra + 16 * i;
-            const int gk = k0 + ca;
-            const bool ok = (m0 + row < M) && (gk < K);
-            cp_async4(smem_u32(As + row * LDAS + ca), ok ? A + size_t(m0 + row) * lda + gk : A, ok ? 4 : 0);
-        }
-        const int cb = tid & 127, rb = tid >> 7;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = rb + 2 * i;
-            const int gn = n0 + cb;
-            const bool ok = (k0 + row < K) && (gn < N);
-            cp_async4(smem_u32(Bs + row * LDBS + cb), ok ? B + size_t(k0 + row) * ldb + gn : B, ok ? 4 : 0);
-        }
+        for (int j = 0; j < 4; ++j) ffma2(acc[i][j], a2, bv[j]);
     }
 }
 
@@ -100,8 +71,8 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
                   const float *__restrict__ B, size_t ldb, float beta, float *__restrict__ C, size_t ldc,
                   int tiles_m, int tiles_n) {
     extern __shared__ __align__(16) float smem_f[];
-    float *As = smem_f;
-    float *Bs = smem_f + STAGES * A_STAGE;
+    float *As = smem_f;                       // [STAGES][BK][LDT]  k-major
+    float *Bs = smem_f + STAGES * TILE;       // [STAGES][BK][LDT]
 
     const int bid = blockIdx.x;
     const int per_band = BAND * tiles_n;
@@ -115,6 +86,59 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;
 
+    // global->shared copy roles.  A: thread owns k-quad (tid&3) of rows (tid>>2) and (tid>>2)+64.
+    const int a_kq = (tid & 3) * 4, a_row = tid >> 2;
+    // B: thread owns float4 column chunk (tid&31) of k rows (tid>>5) and (tid>>5)+8.
+    const int b_c4 = (tid & 31) * 4, b_row = tid >> 5;
+    const bool a_ok0 = m0 + a_row < M, a_ok1 = m0 + a_row + 64 < M;
+    const float *a_src0 = A + size_t(a_ok0 ? m0 + a_row : 0) * lda + a_kq;
+    const float *a_src1 = A + size_t(a_ok1 ? m0 + a_row + 64 : 0) * lda + a_kq;
+    const int b_gn = n0 + b_c4;
+    const float *b_src = B + size_t(b_row) * ldb + (b_gn < N ? b_gn : 0);
+    const int b_bytes_full = b_gn + 3 < N ? 16 : (b_gn < N ? (N - b_gn) * 4 : 0);
+
+    auto load_a = [&](int k0, float4 &r0, float4 &r1) {
+        r0 = make_float4(0.f, 0.f, 0.f, 0.f);
+        r1 = r0;
+        const int gk = k0 + a_kq;
+        if (ALIGNED && gk + 3 < K) {
+            if (a_ok0) r0 = *reinterpret_cast<const float4 *>(a_src0 + k0);
+            if (a_ok1) r1 = *reinterpret_cast<const float4 *>(a_src1 + k0);
+        } else {
+            float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (gk + q < K) {
+                    if (a_ok0) t0[q] = a_src0[k0 + q];
+                    if (a_ok1) t1[q] = a_src1[k0 + q];
+                }
+            r0 = make_float4(t0[0], t0[1], t0[2], t0[3]);
+            r1 = make_float4(t1[0], t1[1], t1[2], t1[3]);
+        }
+    };
+    auto store_a = [&](float *as, const float4 &r0, const float4 &r1) {
+        float *p = as + a_kq * LDT + a_row;
+        p[0] = r0.x; p[LDT] = r0.y; p[2 * LDT] = r0.z; p[3 * LDT] = r0.w;
+        p[64] = r1.x; p[LDT + 64] = r1.y; p[2 * LDT + 64] = r1.z; p[3 * LDT + 64] = r1.w;
+    };
+    auto copy_b = [&](float *bs, int k0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int row = b_row + 8 * i;
+            const bool ok = k0 + row < K;
+            if (ALIGNED) {
+                const int bytes = ok ? b_bytes_full : 0;
+                cp_async16(smem_u32(bs + row * LDT + b_c4), bytes ? b_src + size_t(k0 + 8 * i) * ldb : B, bytes);
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const bool okq = ok && (b_gn + q < N);
+                    cp_async4(smem_u32(bs + row * LDT + b_c4 + q), okq ? B + size_t(k0 + row) * ldb + b_gn + q : B, okq ? 4 : 0);
+                }
+            }
+        }
+    };
+
     unsigned long long acc[8][4];          // acc[i][j2] = (C[i][2*j2], C[i][2*j2+1])
 #pragma unroll
     for (int i = 0; i < 8; ++i)
@@ -122,54 +146,40 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
         for (int j = 0; j < 4; ++j) acc[i][j] = 0ull;
 
     const int KT = (K + BK - 1) / BK;
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < KT) load_slab<ALIGNED>(As + s * A_STAGE, Bs + s * B_STAGE, A, lda, B, ldb, M, N, K, m0, n0, s * BK, tid);
+    {   // prologue: slab 0 into stage 0
+        float4 r0, r1;
+        load_a(0, r0, r1);
+        copy_b(Bs, 0);
         cp_async_commit();
+        store_a(As, r0, r1);
+        cp_async_wait<0>();
+        __syncthreads();
     }
 
     for (int kt = 0; kt < KT; ++kt) {
-        cp_async_wait<STAGES - 2>();
-        __syncthreads();
-        const int s = kt % STAGES;
-        const float *ap = As + s * A_STAGE + (ty * 4) * LDAS;
-        const float *bp = Bs + s * B_STAGE + tx * 4;
-#pragma unroll
-        for (int kk = 0; kk < BK; kk += 4) {
-            float4 a4[8];
-#pragma unroll
-            for (int r = 0; r < 4; ++r) {
-                a4[r] = *reinterpret_cast<const float4 *>(ap + r * LDAS + kk);
-                a4[4 + r] = *reinterpret_cast<const float4 *>(ap + (64 + r) * LDAS + kk);
-            }
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const ulonglong2 b0 = *reinterpret_cast<const ulonglong2 *>(bp + (kk + q) * LDBS);
-                const ulonglong2 b1 = *reinterpret_cast<const ulonglong2 *>(bp + (kk + q) * LDBS + 64);
-                const unsigned long long bv[4] = {b0.x, b0.y, b1.x, b1.y};
-                // j outer / i inner: the 64-bit B pair stays in the operand-reuse cache across the 8 rows, so each
-                // FFMA2 fetches one scalar (A) and one pair (accumulator) from the register file
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const float av = (q == 0) ? a4[i].x : (q == 1) ? a4[i].y : (q == 2) ? a4[i].z : a4[i].w;
-                        ffma2(acc[i][j], pack2(av, av), bv[j]);   // ptxas folds the pack into the .F32 broadcast operand
-                    }
-                }
-            }
-            if (kk == 0) {
-                // queue the copies for slab kt+STAGES-1 once the FMA pipe has work (same idea as dgemm.cu)
-                const int nk = kt + STAGES - 1;
-                if (nk < KT) {
-                    const int ns = nk % STAGES;
-                    load_slab<ALIGNED>(As + ns * A_STAGE, Bs + ns * B_STAGE, A, lda, B, ldb, M, N, K, m0, n0, nk * BK, tid);
-                }
-                cp_async_commit();
-            }
+        const int s = kt & 1;
+        const float *ap = As + s * TILE + ty * 4;
+        const float *bp = Bs + s * TILE + tx * 4;
+        const bool more = kt + 1 < KT;
+        float4 r0, r1;
+        if (more) {                         // slab kt+1: A parked in registers, B by cp.async into the other stage
+            load_a((kt + 1) * BK, r0, r1);
+            copy_b(Bs + (s ^ 1) * TILE, (kt + 1) * BK);
+            cp_async_commit();
         }
+        Frag f[2];
+        load_frag(f[0], ap, bp, 0);
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+            if (kk + 1 < BK) load_frag(f[(kk + 1) & 1], ap, bp, kk + 1);
+            mma_frag(acc, f[kk & 1]);
+        }
+        if (more) {
+            store_a(As + (s ^ 1) * TILE, r0, r1);
+            cp_async_wait<0>();
+        }
+        __syncthreads();
     }
-    cp_async_wait<0>();
 
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll

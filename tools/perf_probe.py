@@ -54,7 +54,24 @@ def main():
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
                 del a, b, c
-    l.rla_set_tuning(b"dgemm_cfg", 0)
+    if "pcie" in which:
+        nbytes = 1 << 30
+        h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        h2 = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+        d2 = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        s2 = torch.cuda.Stream()
+        def h2d(): d.copy_(h, non_blocking=True)
+        def d2h(): h.copy_(d, non_blocking=True)
+        def both():
+            d.copy_(h, non_blocking=True)
+            with torch.cuda.stream(s2):
+                h2.copy_(d2, non_blocking=True)
+            torch.cuda.current_stream().wait_stream(s2)
+        for name, fn, mult in (("h2d", h2d, 1), ("d2h", d2h, 1), ("bidir", both, 2)):
+            best, med = timed(fn, 5)
+            print(json.dumps(dict(op="pcie_" + name, gib=1, ms=best, gbs=mult * nbytes / best * 1e-6)), flush=True)
+    l.rla_set_tuning(b"dgemm_cfg", -1)
     if "lu" in which:
         for dt, fn, name in ((torch.float64, l.rla_dgetrf_dev, "dgetrf"), (torch.float32, l.rla_sgetrf_dev, "sgetrf")):
             for n in (256, 1024, 2048, 4096, 8192, 16384, 32768):
