@@ -79,6 +79,13 @@ RLA_API int rla_sgetrf(size_t n, float *lu, size_t *perm);      /* T = f32: FLT_
 RLA_API int rla_dgetrs(size_t n, const double *lu, const size_t *perm, double *b);
 RLA_API int rla_sgetrs(size_t n, const float *lu, const size_t *perm, float *b);
 
+/* PartialPivLu::inverse (lu.rs:251-285) -- SURVEY 8f "next" row.  The reference performs n solves of unit
+ * vectors; here X = U^-1 L^-1 P is a blocked multi-RHS substitution on the GEMM kernels (2n^3 flops).  n <= 64
+ * keeps the reference's exact per-column operation order (bit-identical).  inv: n x n row-major contiguous,
+ * written in full.  RLA_ERR_SINGULAR when some |u_ii| < epsilon (back_substitution's test, mod.rs:333-336). */
+RLA_API int rla_dgetri(size_t n, const double *lu, const size_t *perm, double *inv);
+RLA_API int rla_sgetri(size_t n, const float *lu, const size_t *perm, float *inv);
+
 /* Factorisation kept resident in HBM for repeated solves (PartialPivLu is built for "multiple
  * such linear systems involving the same A", lu.rs:203-206).  rla_dgetrf_keep = rla_dgetrf
  * that also returns a handle; rla_lu_solve = rla_dgetrs without re-uploading lu. */
@@ -124,6 +131,12 @@ RLA_API int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t 
                    double *d_b, int32_t *d_info, void *stream);
 RLA_API int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm,
                    float *d_b, int32_t *d_info, void *stream);
+
+/* inverse from a device-resident factorisation: x (n x n, row stride ldx) <- A^-1; d_info as rla_dgetrs_dev */
+RLA_API int rla_dgetri_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm, double *x, size_t ldx,
+                   int32_t *d_info, void *stream);
+RLA_API int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, float *x, size_t ldx,
+                   int32_t *d_info, void *stream);
 
 /* Building blocks of the 1D block-cyclic multi-GPU LU (driven by rulinalg_b200/sharded_lu.py, one
  * process per GPU, panel broadcast over NCCL).  Local matrix: n rows x ncols_loc columns, row stride ld; the

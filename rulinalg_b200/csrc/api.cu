@@ -361,6 +361,32 @@ int getrs_host(size_t n, const T *lu, const size_t *perm, T *b) {
     return getrs_core<T>(n, dA, ld, dP, b);
 }
 
+template <typename T>
+int getri_host(size_t n, const T *lu, const size_t *perm, T *inv) {
+    if (n == 0) return RLA_OK;
+    if (!lu || !perm || !inv) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dC.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dPerm.ensure(n * sizeof(int64_t)));
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    T *dA = static_cast<T *>(cx.dA.p), *dX = static_cast<T *>(cx.dC.p);
+    int64_t *dP = static_cast<int64_t *>(cx.dPerm.p);
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p), *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    RLA_TRY(upload_matrix(dA, ld, lu, n, n, n, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(dP, perm, n * sizeof(int64_t), cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(getri_launch<T>(n, dA, ld, dP, dX, ld, dInfo, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*hInfo != 0) return RLA_ERR_SINGULAR;
+    RLA_TRY(download_matrix(inv, n, dX, ld, n, n, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
 }  // namespace
 
 void note_cuda_error(cudaError_t e) { tl_last_cuda = e; }
@@ -391,6 +417,19 @@ int rla_dgetrf(size_t n, double *lu, size_t *perm) { return getrf_host<double>(n
 int rla_sgetrf(size_t n, float *lu, size_t *perm) { return getrf_host<float>(n, lu, perm, nullptr, nullptr, nullptr); }
 int rla_dgetrs(size_t n, const double *lu, const size_t *perm, double *b) { return getrs_host<double>(n, lu, perm, b); }
 int rla_sgetrs(size_t n, const float *lu, const size_t *perm, float *b) { return getrs_host<float>(n, lu, perm, b); }
+
+int rla_dgetri(size_t n, const double *lu, const size_t *perm, double *inv) { return getri_host<double>(n, lu, perm, inv); }
+int rla_sgetri(size_t n, const float *lu, const size_t *perm, float *inv) { return getri_host<float>(n, lu, perm, inv); }
+int rla_dgetri_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm, double *x, size_t ldx, int32_t *d_info,
+                   void *stream) {
+    RLA_TRY(ensure_ctx());
+    return getri_launch<double>(n, lu, ld, d_perm, x, ldx, d_info, pick_stream(stream));
+}
+int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, float *x, size_t ldx, int32_t *d_info,
+                   void *stream) {
+    RLA_TRY(ensure_ctx());
+    return getri_launch<float>(n, lu, ld, d_perm, x, ldx, d_info, pick_stream(stream));
+}
 
 int rla_dgetrf_keep(size_t n, double *lu, size_t *perm, rla_lu_handle **out) {
     if (!out) return RLA_ERR_INVALID;
@@ -543,7 +582,7 @@ int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, ui
 int rla_set_tuning(const char *key, int value) {
     if (!key) return RLA_ERR_INVALID;
     if (strcmp(key, "dgemm_cfg") == 0) {
-        if (value < -1 || value > 1) return RLA_ERR_INVALID;
+        if (value < -1 || value > 3) return RLA_ERR_INVALID;
         g_dgemm_cfg = value;
         return RLA_OK;
     }

@@ -10,6 +10,7 @@
 //     cfg 0  128x64  tile, 4 warps (2x2), 3-stage ring, TWO CTAs per SM: while one CTA sits at its
 //            slab barrier, issues its cp.async or runs its epilogue, the other keeps the DMMA pipe fed.
 //     cfg 1  128x128 tile, 8 warps (2x4), 4-stage ring, one CTA per SM.
+//     cfg 2  as cfg 1 with k-slab 32 and a 3-stage ring (half the barriers; +0.4 % on long-k products).
 //   A (k contiguous) and B (n contiguous) k-slabs of 16 are staged global->shared with 16-byte
 //   cp.async (LDGSTS), one __syncthreads per slab; the copies for slab kt+S-1 are issued AFTER the
 //   first quarter of slab kt's DMMAs so the tensor pipe never waits on address arithmetic.  Source
@@ -27,14 +28,13 @@
 namespace rla {
 namespace {
 
-constexpr int BK = 16;
-constexpr int LDAS = BK + 4;             // padded A row (doubles)
 constexpr int BAND = 16;                 // tile-rows per raster band
 
-template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_>
+template <int BM_, int BN_, int WM_, int WN_, int STAGES_, int MINB_, int BK_ = 16>
 struct Cfg {
-    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_;
+    static constexpr int BM = BM_, BN = BN_, WM = WM_, WN = WN_, STAGES = STAGES_, MINB = MINB_, BK = BK_;
     static constexpr int THREADS = WM * WN * 32;
+    static constexpr int LDAS = BK + 4;  // padded A row (doubles): word stride 2*BK+8 == 8 (mod 32) for BK in {16,32}
     static constexpr int LDBS = BN + 4;
     static constexpr int A_STAGE = BM * LDAS;
     static constexpr int B_STAGE = BK * LDBS;
@@ -46,15 +46,17 @@ struct Cfg {
 };
 using CfgSmall = Cfg<128, 64, 2, 2, 3, 2>;
 using CfgLarge = Cfg<128, 128, 2, 4, 4, 1>;
+using CfgLargeK32 = Cfg<128, 128, 2, 4, 3, 1, 32>;
+using CfgSmallK32 = Cfg<128, 64, 2, 2, 2, 2, 32>;
 
 // Per-thread copy plan for the aligned (16-byte) path.  Thread `tid` always copies chunk column
 // `tid % chunks_per_row` of rows `tid / chunks_per_row + i * rows_per_pass`: one base pointer per
 // operand plus a constant row stride, so the per-slab address arithmetic is a handful of IMADs.
 template <class C>
 struct CopyPlan {
-    static constexpr int ACH = BK / 2, A_ROWS = C::THREADS / ACH;        // A: chunks per row, rows per pass
+    static constexpr int ACH = C::BK / 2, A_ROWS = C::THREADS / ACH;        // A: chunks per row, rows per pass
     static constexpr int BCH = C::BN / 2, B_ROWS = C::THREADS / BCH;     // B
-    static_assert(A_ROWS * C::A_CHUNKS == C::BM && B_ROWS * C::B_CHUNKS == BK, "copy plan");
+    static_assert(A_ROWS * C::A_CHUNKS == C::BM && B_ROWS * C::B_CHUNKS == C::BK, "copy plan");
     const double *a_src;     // A + (m0 + row0)*lda + 2*ch
     const double *b_src;     // B + row0*ldb + n0 + 2*ch
     size_t a_step, b_step;   // elements between passes (A_ROWS*lda, B_ROWS*ldb)
@@ -78,7 +80,7 @@ __device__ __forceinline__ void issue_slab(const CopyPlan<C> &p, uint32_t as_bas
 #pragma unroll
         for (int i = 0; i < C::A_CHUNKS; ++i) {
             const int bytes = ((p.a_valid >> i) & 1u) ? abytes : 0;
-            cp_async16(as_base + p.a_dst + i * (P::A_ROWS * LDAS * 8), bytes ? asrc + i * p.a_step : A, bytes);
+            cp_async16(as_base + p.a_dst + i * (P::A_ROWS * C::LDAS * 8), bytes ? asrc + i * p.a_step : A, bytes);
         }
         const double *bsrc = p.b_src + size_t(k0) * ldb;
 #pragma unroll
@@ -89,13 +91,13 @@ __device__ __forceinline__ void issue_slab(const CopyPlan<C> &p, uint32_t as_bas
         }
     } else {
         // 8-byte path for odd leading dimensions / unaligned bases (bounds evaluated per element)
-        constexpr int AE = C::BM * BK / C::THREADS, BE = BK * C::BN / C::THREADS;
+        constexpr int AE = C::BM * C::BK / C::THREADS, BE = C::BK * C::BN / C::THREADS;
 #pragma unroll
         for (int i = 0; i < AE; ++i) {
             const int e = tid + i * C::THREADS;
-            const int row = e / BK, kk = e % BK;
+            const int row = e / C::BK, kk = e % C::BK;
             const bool ok = (m0 + row < M) && (k0 + kk < K);
-            cp_async8(as_base + (row * LDAS + kk) * 8, ok ? A + size_t(m0 + row) * lda + k0 + kk : A, ok ? 8 : 0);
+            cp_async8(as_base + (row * C::LDAS + kk) * 8, ok ? A + size_t(m0 + row) * lda + k0 + kk : A, ok ? 8 : 0);
         }
 #pragma unroll
         for (int i = 0; i < BE; ++i) {
@@ -111,7 +113,7 @@ template <class C>
 __device__ __forceinline__ void mma_k4(double (&acc)[8][4][2], const double *ap, const double *bp, int kk) {
     double af[8], bf[4];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) af[i] = ap[i * 8 * LDAS + kk];
+    for (int i = 0; i < 8; ++i) af[i] = ap[i * 8 * C::LDAS + kk];
 #pragma unroll
     for (int j = 0; j < 4; ++j) bf[j] = bp[kk * C::LDBS + j * 8];
 #pragma unroll
@@ -149,7 +151,7 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
         using P = CopyPlan<C>;
         const int arow = tid / P::ACH, ach = tid % P::ACH;
         plan.a_k = 2 * ach;
-        plan.a_dst = (arow * LDAS + 2 * ach) * 8;
+        plan.a_dst = (arow * C::LDAS + 2 * ach) * 8;
         plan.a_step = size_t(P::A_ROWS) * lda;
         plan.a_valid = 0;
 #pragma unroll
@@ -171,19 +173,19 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-    const int KT = (K + BK - 1) / BK;
-    const int KT_FULL = K / BK;                  // slabs needing no k-bound checks
+    const int KT = (K + C::BK - 1) / C::BK;
+    const int KT_FULL = K / C::BK;                  // slabs needing no k-bound checks
     const uint32_t as_u32 = smem_u32(As), bs_u32 = smem_u32(Bs);
 
 #pragma unroll
     for (int s = 0; s < C::STAGES - 1; ++s) {
         if (s < KT)
-            issue_slab<C, ALIGNED>(plan, as_u32 + s * C::A_STAGE * 8, bs_u32 + s * C::B_STAGE * 8, s * BK, K, ldb,
+            issue_slab<C, ALIGNED>(plan, as_u32 + s * C::A_STAGE * 8, bs_u32 + s * C::B_STAGE * 8, s * C::BK, K, ldb,
                                    s < KT_FULL, A, B, lda, M, N, m0, n0, tid);
         cp_async_commit();
     }
 
-    const double *a_frag_base = As + (wm * 64 + g) * LDAS + t;
+    const double *a_frag_base = As + (wm * 64 + g) * C::LDAS + t;
     const double *b_frag_base = Bs + t * C::LDBS + wn * 32 + g;
 
     int stage = 0;
@@ -198,14 +200,13 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
             if (nk < KT) {
                 int ns = stage + C::STAGES - 1;
                 if (ns >= C::STAGES) ns -= C::STAGES;
-                issue_slab<C, ALIGNED>(plan, as_u32 + ns * C::A_STAGE * 8, bs_u32 + ns * C::B_STAGE * 8, nk * BK, K, ldb,
+                issue_slab<C, ALIGNED>(plan, as_u32 + ns * C::A_STAGE * 8, bs_u32 + ns * C::B_STAGE * 8, nk * C::BK, K, ldb,
                                        nk < KT_FULL, A, B, lda, M, N, m0, n0, tid);
             }
             cp_async_commit();
         }
-        mma_k4<C>(acc, ap, bp, 4);
-        mma_k4<C>(acc, ap, bp, 8);
-        mma_k4<C>(acc, ap, bp, 12);
+#pragma unroll
+        for (int kk = 4; kk < C::BK; kk += 4) mma_k4<C>(acc, ap, bp, kk);
         if (++stage == C::STAGES) stage = 0;
     }
     cp_async_wait<0>();
@@ -328,11 +329,13 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     // -1 (default): 128x128 tiles for long-k products that fill the machine several times over (2 % faster
     // there), the 2-CTA/SM 128x64 shape otherwise (rank-k updates, small and skinny products)
     int cfg = g_dgemm_cfg;
-    if (cfg < 0) cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? 1 : 0;
+    if (cfg < 0) cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? (aligned ? 2 : 1) : 0;
     if (cfg == 1) {
         return aligned ? launch_cfg<CfgLarge, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                        : launch_cfg<CfgLarge, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     }
+    if (cfg == 2 && aligned) return launch_cfg<CfgLargeK32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    if (cfg == 3 && aligned) return launch_cfg<CfgSmallK32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     return aligned ? launch_cfg<CfgSmall, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                    : launch_cfg<CfgSmall, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }

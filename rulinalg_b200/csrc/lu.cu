@@ -501,6 +501,68 @@ trsm_unit_lower_kernel(const T *__restrict__ L, size_t ldl, int jb, T *__restric
     }
 }
 
+// B <- U^-1 B, U = jb x jb upper NON-unit (jb <= 64): same 4-threads-per-column scheme, k descending.
+// Diagonal reciprocals are formed once (the singularity test |u_ii| < eps is done by the caller).
+template <typename T>
+__global__ void __launch_bounds__(TRSM_THREADS)
+trsm_upper_kernel(const T *__restrict__ U, size_t ldu, int jb, T *__restrict__ B, size_t ldb, int ncols,
+                  const int32_t *__restrict__ info) {
+    if (*info != 0) return;
+    __shared__ T Us[PW * (PW + 1)];
+    __shared__ T rdiag[PW];
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < PW * PW; idx += TRSM_THREADS) {
+        const int r = idx / PW, c = idx - r * PW;
+        T v = (r == c) ? T(1) : T(0);
+        if (r < jb && c < jb && c >= r) v = U[size_t(r) * ldu + c];
+        Us[r * (PW + 1) + c] = v;
+    }
+    __syncthreads();
+    if (tid < PW) rdiag[tid] = T(1) / Us[tid * (PW + 1) + tid];
+    __syncthreads();
+    const int lane = tid & 31;
+    const int r = lane & 3;
+    const int col = blockIdx.x * TRSM_COLS + (tid >> 5) * 8 + (lane >> 2);
+    const bool ok = col < ncols;
+    T x[PW / 4];
+#pragma unroll
+    for (int ii = 0; ii < PW / 4; ++ii) {
+        const int i = 4 * ii + r;
+        x[ii] = (ok && i < jb) ? B[size_t(i) * ldb + col] : T(0);
+    }
+    const T *Ur = Us + r * (PW + 1);
+#pragma unroll
+    for (int k = PW - 1; k >= 0; --k) {
+        if (r == (k & 3)) x[k >> 2] *= rdiag[k];
+        const T xk = __shfl_sync(0xffffffffu, x[k >> 2], (lane & ~3) | (k & 3));
+#pragma unroll
+        for (int ii = 0; ii <= (k >> 2); ++ii) {
+            if (ii < (k >> 2) || r < (k & 3)) x[ii] -= Ur[(4 * ii) * (PW + 1) + k] * xk;
+        }
+    }
+#pragma unroll
+    for (int ii = 0; ii < PW / 4; ++ii) {
+        const int i = 4 * ii + r;
+        if (ok && i < jb) B[size_t(i) * ldb + col] = x[ii];
+    }
+}
+
+// X <- P as a dense matrix: X[r][c] = (r == perm[c])   (column c of the inverse is solve(e_c), and P e_c = e_perm[c])
+template <typename T>
+__global__ void perm_matrix_kernel(T *__restrict__ X, size_t ldx, int n, const int64_t *__restrict__ perm) {
+    const size_t idx = size_t(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (idx >= size_t(n) * n) return;
+    const int r = int(idx / n), c = int(idx - size_t(r) * n);
+    X[size_t(r) * ldx + c] = (int64_t(r) == perm[c]) ? T(1) : T(0);
+}
+// back_substitution's test (src/matrix/mod.rs:333-336) for every diagonal entry; reports the LAST failing row
+// like the reference's descending loop would hit first
+template <typename T>
+__global__ void diag_check_kernel(const T *__restrict__ lu, size_t ld, int n, int32_t *__restrict__ info) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && fabs(lu[size_t(i) * ld + i]) < Eps<T>::v()) atomicMax(info, i + 1);
+}
+
 // rowid <- plan applied to it (the row-origin vector from which `perm` is produced)
 __global__ void __launch_bounds__(256)
 rowid_apply_kernel(const LaswpPlan *__restrict__ plan, int32_t *__restrict__ rowid, const int32_t *__restrict__ info) {
@@ -751,6 +813,53 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
 
 template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
 template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
+
+// PartialPivLu::inverse (lu.rs:251-285) as a blocked multi-RHS solve: X = U^-1 L^-1 P with all n unit vectors at once
+// (SURVEY 8f rank 1).  The reference performs n separate solves; this is 2n^3 flops on the GEMM kernels instead.
+template <typename T>
+int getri_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *x, size_t ldx, int32_t *d_info,
+                 cudaStream_t st) {
+    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    if (n == 0) return RLA_OK;
+    if (n <= 64) return getri_small_launch<T>(n, lu, ld, d_perm, x, ldx, d_info, st);
+    diag_check_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(lu, ld, n, d_info);
+    RLA_LAUNCHED();
+    {
+        const size_t total = size_t(n) * n;
+        perm_matrix_kernel<T><<<unsigned((total + 255) / 256), 256, 0, st>>>(x, ldx, n, d_perm);
+        RLA_LAUNCHED();
+    }
+    // L Y = P : forward, outer blocks of 256
+    for (int J0 = 0; J0 < n; J0 += OUTER_W) {
+        const int w = min(OUTER_W, n - J0);
+        RLA_TRY(trsm_block<T>(lu + size_t(J0) * ld + J0, ld, w, x + size_t(J0) * ldx, ldx, n, d_info, st));
+        if (J0 + w < n)
+            RLA_TRY(gemm_update<T>(size_t(n - J0 - w), size_t(w), size_t(n), lu + size_t(J0 + w) * ld + J0, ld,
+                                   x + size_t(J0) * ldx, ldx, x + size_t(J0 + w) * ldx, ldx, st));
+    }
+    // U X = Y : backward
+    const int nblk = (n + OUTER_W - 1) / OUTER_W;
+    for (int bI = nblk - 1; bI >= 0; --bI) {
+        const int J0 = bI * OUTER_W, w = min(OUTER_W, n - J0);
+        const int nsub = (w + PW - 1) / PW;
+        for (int sb = nsub - 1; sb >= 0; --sb) {
+            const int kb = sb * PW, jb = min(PW, w - kb);
+            trsm_upper_kernel<T><<<(n + TRSM_COLS - 1) / TRSM_COLS, TRSM_THREADS, 0, st>>>(
+                lu + size_t(J0 + kb) * ld + J0 + kb, ld, jb, x + size_t(J0 + kb) * ldx, ldx, n, d_info);
+            RLA_LAUNCHED();
+            if (kb > 0)   // rows of this outer block above the sub-block
+                RLA_TRY(gemm_update<T>(size_t(kb), size_t(jb), size_t(n), lu + size_t(J0) * ld + J0 + kb, ld,
+                                       x + size_t(J0 + kb) * ldx, ldx, x + size_t(J0) * ldx, ldx, st));
+        }
+        if (J0 > 0)
+            RLA_TRY(gemm_update<T>(size_t(J0), size_t(w), size_t(n), lu + J0, ld, x + size_t(J0) * ldx, ldx, x, ldx, st));
+    }
+    return RLA_OK;
+}
+template int getri_launch<double>(size_t, const double *, size_t, const int64_t *, double *, size_t, int32_t *, cudaStream_t);
+template int getri_launch<float>(size_t, const float *, size_t, const int64_t *, float *, size_t, int32_t *, cudaStream_t);
 
 // ---------------------------------------------------------------------------------------------
 // Building blocks of the 1D block-cyclic multi-GPU LU (rulinalg_b200/sharded_lu.py drives them).

@@ -37,18 +37,22 @@ __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, 
 
 constexpr int SMALL_N = 64;
 
+// One warp per right-hand side.  batched == 0: rhs = b[0..n), solved in place.  batched == 1 (inverse): block c
+// solves rhs = e_c and writes column c of the n x n matrix b (row stride bs) -- PartialPivLu::inverse's loop
+// (lu.rs:272-282) with every column in the reference's exact operation order.
 template <typename T>
 __global__ void __launch_bounds__(32)
 getrs_small_kernel(int n, const T *__restrict__ lu, size_t ld, const int64_t *__restrict__ perm, T *__restrict__ b,
-                   int32_t *__restrict__ info) {
+                   size_t bs, int batched, int32_t *__restrict__ info) {
     __shared__ T x[SMALL_N];
     __shared__ T m[SMALL_N * (SMALL_N + 1)];
     const int lane = threadIdx.x;
+    const int col = blockIdx.x;
     for (int idx = lane; idx < n * n; idx += 32) {
         const int r = idx / n, c = idx - r * n;
         m[r * (SMALL_N + 1) + c] = lu[size_t(r) * ld + c];
     }
-    for (int i = lane; i < n; i += 32) x[int(perm[i])] = b[i];
+    for (int i = lane; i < n; i += 32) x[int(perm[i])] = batched ? (i == col ? T(1) : T(0)) : b[i];
     __syncwarp();
     // forward: column sweep; each row's sum grows in ascending k exactly like the reference fold
     T sum0 = T(0), sum1 = T(0);
@@ -92,7 +96,9 @@ getrs_small_kernel(int n, const T *__restrict__ lu, size_t ld, const int64_t *__
         __syncwarp();
     }
     if (!bad)
-        for (int i = lane; i < n; i += 32) b[i] = x[i];
+        for (int i = lane; i < n; i += 32) {
+            if (batched) b[size_t(i) * bs + col] = x[i]; else b[i] = x[i];
+        }
 }
 
 // out[perm[i]] = in[i]
@@ -247,7 +253,7 @@ int getrs_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *d_
     RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
     if (n == 0) return RLA_OK;
     if (n <= SMALL_N) {
-        getrs_small_kernel<T><<<1, 32, 0, st>>>(n, lu, ld, d_perm, d_b, d_info);
+        getrs_small_kernel<T><<<1, 32, 0, st>>>(n, lu, ld, d_perm, d_b, 0, 0, d_info);
         RLA_LAUNCHED();
         return RLA_OK;
     }
@@ -263,6 +269,18 @@ int getrs_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *d_
     RLA_LAUNCHED();
     return RLA_OK;
 }
+
+// inverse of a factorisation with n <= 64: n exact-order solves, one warp each (bit-identical to the reference)
+template <typename T>
+int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *x, size_t ldx, int32_t *d_info,
+                       cudaStream_t st) {
+    if (n <= 0 || n > SMALL_N) return RLA_ERR_INVALID;
+    getrs_small_kernel<T><<<n, 32, 0, st>>>(n, lu, ld, d_perm, x, ldx, 1, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+template int getri_small_launch<double>(int, const double *, size_t, const int64_t *, double *, size_t, int32_t *, cudaStream_t);
+template int getri_small_launch<float>(int, const float *, size_t, const int64_t *, float *, size_t, int32_t *, cudaStream_t);
 
 template int getrs_launch<double>(size_t, const double *, size_t, const int64_t *, double *, double *, int32_t *,
                                   int32_t *, cudaStream_t);

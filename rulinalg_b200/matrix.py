@@ -352,14 +352,15 @@ class PartialPivLu:
         return Vector(x)
 
     def inverse(self) -> Matrix:
-        # lu.rs:251-285: n solves of unit vectors, written column by column
+        # lu.rs:251-285 (n solves of unit vectors) as ONE blocked multi-RHS solve on the device (rla_?getri);
+        # n <= 64 keeps the reference's exact per-column order
         n = self.lu.rows()
         dt = self.lu._arr.dtype
-        inv = np.zeros((n, n), dtype=dt)
-        for i in range(n):
-            e = np.zeros(n, dtype=dt)
-            e[i] = 1
-            inv[:, i] = self.solve(Vector(e)).data()
+        inv = np.empty((n, n), dtype=dt)
+        pre = _dtype_pre(dt)
+        st = getattr(_lib.lib(), f"rla_{pre}getri")(n, self.lu.as_ptr(), self.p.perm().ctypes.data, inv.ctypes.data)
+        if _lib.check(st) == _lib.RLA_ERR_SINGULAR:
+            raise Error(ErrorKind.DivByZero, _TRI_SINGULAR_MSG)
         return Matrix._from_array(inv)
 
     def det(self):

@@ -415,6 +415,47 @@ def test_lu_full_size_properties(rla, oracle):
     assert st == 0 and np.array_equal(x2, x)
 
 
+@pytest.mark.parametrize("n", [1, 3, 17, 64])
+def test_inverse_bit_exact_small(rla, oracle, n):
+    # PartialPivLu::inverse = n solves of unit vectors (lu.rs:251-285); n <= 64 keeps the exact operation order
+    a = oracle.fill_uniform((n, n), 21, lo=-1.0, scale=2.0) + np.eye(n)
+    ref_lu, ref_perm = oracle.lu_decompose(a)
+    inv = decompose(rla, a).inverse().to_numpy()
+    oracle.assert_matrix_eq(inv, oracle.lu_inverse(ref_lu, ref_perm), comp="exact")
+
+
+@pytest.mark.parametrize("dtype,n", [(np.float64, 65), (np.float64, 300), (np.float64, 700), (np.float64, 1024), (np.float32, 300)])
+def test_inverse_blocked_vs_oracle(rla, oracle, dtype, n):
+    # blocked multi-RHS inverse (rla_?getri): residual and distance to the reference's column-by-column result
+    a = oracle.fill_uniform((n, n), 12, dtype)
+    f = decompose(rla, a)
+    inv = f.inverse().to_numpy().astype(np.float64)
+    a64 = a.astype(np.float64)
+    u = U(dtype)
+    kappa = np.linalg.cond(a64, 1)
+    resid = np.max(np.abs(a64 @ inv - np.eye(n)))
+    assert resid <= 8 * n * u * kappa, (resid, kappa)
+    if dtype == np.float64:
+        ref_lu, ref_perm = oracle.lu_decompose(a, fast=True)
+        ref_inv = oracle.lu_inverse(ref_lu, ref_perm)
+        assert np.max(np.abs(inv - ref_inv)) / np.max(np.abs(ref_inv)) <= 8 * n * u * kappa
+    # Matrix::inverse wrapper (impl_mat.rs:386-388) takes the same path
+    inv2 = rla.Matrix.from_numpy(a).inverse().to_numpy()
+    assert np.array_equal(inv2.astype(np.float64), inv)
+
+
+def test_inverse_singular_is_div_by_zero(rla):
+    n = 100
+    lu = np.triu(np.ones((n, n))) + np.tril(np.full((n, n), 0.5), -1)
+    lu[70, 70] = 1e-17
+    bad = rla.PartialPivLu(rla.Matrix.from_numpy(lu), rla.PermutationMatrix.identity(n))
+    with pytest.raises(rla.Error) as ei:
+        bad.inverse()
+    assert ei.value.kind() == rla.ErrorKind.DivByZero
+    with pytest.raises(rla.Panic):
+        rla.Matrix.ones(2, 3).inverse()
+
+
 def test_launch_counter_and_version(rla):
     l = rla.lib()
     l.rla_launch_count_reset()

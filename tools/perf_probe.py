@@ -38,6 +38,7 @@ def main():
     if "dgemm" in which or "sgemm" in which:
         shapes = [(n, n, n) for n in (512, 1024, 2048, 4096, 8192, 16384)] + [(65536, 256, 256), (4096, 32768, 32768), (16384, 256, 16384), (16384, 64, 192)]
         for name, dt, fn, cfg in (("dgemm", torch.float64, l.rla_dgemm_dev, 0), ("dgemm", torch.float64, l.rla_dgemm_dev, 1),
+                                  ("dgemm", torch.float64, l.rla_dgemm_dev, 2), ("dgemm", torch.float64, l.rla_dgemm_dev, 3),
                                   ("sgemm", torch.float32, l.rla_sgemm_dev, 0)):
             if name not in which:
                 continue
@@ -106,6 +107,11 @@ def main():
                     sbest, smed = timed(solve, 5, warm=1)
                     rec = dict(op="dgetrs", n=n, ms=sbest, gbs=8 * n * n / sbest * 1e-6, info=int(info.item()))
                     print(json.dumps(rec), flush=True)
+                if name == "dgetrf" and n in (1024, 4096, 8192):
+                    x = torch.empty(n, n, dtype=dt, device="cuda")
+                    ibest, _ = timed(lambda: rla.check(l.rla_dgetri_dev(n, a.data_ptr(), n, perm.data_ptr(), x.data_ptr(), n, info.data_ptr(), s)), 3, warm=1)
+                    print(json.dumps(dict(op="dgetri", n=n, ms=ibest, tflops=2 * n ** 3 / ibest * 1e-9, info=int(info.item()))), flush=True)
+                    del x
                 del a0, a
                 torch.cuda.empty_cache()
 
