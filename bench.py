@@ -155,7 +155,7 @@ def run_reference(args):
         "e2e": {"value": gflops, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(line)
     return 0
 
 
@@ -352,7 +352,7 @@ def run_ours(args):
     if sampler:
         sampler.stop()
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        emit_line(line)
     if world > 1:
         dist.destroy_process_group()
     return 0
@@ -445,11 +445,46 @@ def dist_lu_extra(rla, l, torch, dist, world, rank, dev, n=32768):
                                   "info": int(info.item())}}
 
 
+class _StdoutGuard:
+    """Everything any library writes to fd 1 during the run (e.g. NCCL's version banner) goes to stderr;
+    only the final JSON line is written to the real stdout."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        self.real = os.fdopen(self.saved, "w")
+        return self
+
+    def emit(self, text):
+        self.real.write(text + "\n")
+        self.real.flush()
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        return False
+
+
+_GUARD = None
+
+
+def emit_line(line):
+    text = json.dumps(line)
+    if _GUARD is not None:
+        _GUARD.emit(text)
+    else:
+        print(text, flush=True)
+
+
 def main():
+    global _GUARD
     args = parse()
-    if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+    with _StdoutGuard() as g:
+        _GUARD = g
+        if args.impl == "reference":
+            return run_reference(args)
+        return run_ours(args)
 
 
 if __name__ == "__main__":
