@@ -149,6 +149,8 @@ RLA_API int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *
  *                  U12 = L11^-1 A12 and A22 -= L21 U12 on local columns [c0,c1)
  *   rowid_*      : the row-origin vector every rank carries; perm_from_rowid gives PartialPivLu.p.perm */
 RLA_API size_t rla_lu_plan_bytes(void);
+/* development aid: with rla_set_tuning("lu_dbg", 8) the last panel launch records 64 x 8 globaltimer stamps */
+RLA_API int rla_debug_lu_trace(unsigned long long *host512);
 RLA_API int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w,
                              int32_t *d_info, void *d_plan, void *stream);
 RLA_API int rla_dlu_laswp_dev(double *a_loc, size_t ld, size_t w, const void *d_plan, const int32_t *d_info,

@@ -539,6 +539,7 @@ int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
                                static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
 }
 size_t rla_lu_plan_bytes(void) { return lu_plan_bytes(); }
+int rla_debug_lu_trace(unsigned long long *host512) { return lu_trace_fetch(host512); }
 int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w, int32_t *d_info,
                              void *d_plan, void *stream) {
     RLA_TRY(ensure_ctx());

@@ -68,6 +68,7 @@ template <typename T>
 int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *x, size_t ldx, int32_t *d_info,
                        cudaStream_t st);
 size_t lu_plan_bytes();
+int lu_trace_fetch(unsigned long long *host512);
 template <typename T>
 int lu_factor_block_dev(int n, T *a_loc, size_t ld, int row0, int lcol0, int w, int32_t *d_info, void *d_plan,
                         LuWorkspace &ws, cudaStream_t st);

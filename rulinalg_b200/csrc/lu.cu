@@ -54,6 +54,23 @@ __device__ __forceinline__ bool cand_better(T va, int ia, T vb, int ib) {
     return (va > vb) || (va == vb && ia < ib);
 }
 
+// Candidate = (key, idx): key = bit pattern of |value| as an f64 (order-preserving for non-negative values; 0 with
+// idx INT_MAX = "no candidate").  Winner = max key, ties -> lowest row index (the reference's strict '>' scan).
+// Three redux.sync instead of 15 dependent shuffles: the shuffle version cost ~0.5 us per column.
+__device__ __forceinline__ unsigned long long key_of(double absval) {
+    return absval < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(absval);
+}
+__device__ __forceinline__ void warp_argmax(unsigned long long &key, int &idx, unsigned &winner_mask) {
+    const unsigned hi = unsigned(key >> 32), lo = unsigned(key);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool top = (hi == mhi) && (lo == mlo);
+    const int midx = __reduce_min_sync(0xffffffffu, top ? idx : INT_MAX);
+    winner_mask = __ballot_sync(0xffffffffu, top && idx == midx);
+    key = ((unsigned long long)mhi << 32) | mlo;
+    idx = midx;
+}
+
 // -------------------------------------------------------------------------------------------
 // Panel factorisation of A[J:n, J:J+jb].  Cooperative grid of G "row" CTAs + 1 "hub" CTA.
 // Row CTA b keeps rows [J + b*R, J + (b+1)*R) of the panel in shared memory.
@@ -110,7 +127,14 @@ struct PanelScratch {
     PlanState *state;
     LaswpPlan *plan;
     int32_t *rowid;
+    unsigned long long *trace;       // optional [64 columns][8 stamps] of globaltimer ns (lu_dbg bit 3), else nullptr
 };
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define TRACE(slot) do { if (sc.trace && tid == 0) sc.trace[c * 8 + (slot)] = gtime(); } while (0)
 constexpr int HUB_ROOT_WARPS = 5;                 // 160 threads >= G
 constexpr int HUB_ROOT_THREADS = HUB_ROOT_WARPS * 32;
 constexpr int HUB_SWAP_T0 = 192;                  // warps 6..15 apply the interchanges
@@ -123,7 +147,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
     extern __shared__ __align__(16) unsigned char panel_smem[];
     T *s = reinterpret_cast<T *>(panel_smem);
     __shared__ T prow_s[PW];
-    __shared__ T red_abs[2][PANEL_THREADS / 32];
+    __shared__ unsigned long long red_key[2][PANEL_THREADS / 32];
     __shared__ int red_idx[2][PANEL_THREADS / 32];
     __shared__ int red_win[2][PANEL_THREADS / 32];
     __shared__ T sh_abs;
@@ -156,7 +180,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             for (int c = 0; c < jb; ++c) {
                 const int par = c & 1;
                 const unsigned tag = tag_base + unsigned(c) + 1u;
-                T gv = T(-1);
+                unsigned long long gk = 0ull;
                 int gi = INT_MAX, gw = 0;
                 // whole warps poll: lanes past G re-read packet G-1 (a duplicate candidate is harmless),
                 // so no polling warp is ever partially active
@@ -166,32 +190,28 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                     do {
                         msg_load(sc.packets + par * GMAX + q, lo, hi);
                     } while (unsigned(hi >> 32) != tag);
-                    gv = T(__longlong_as_double((long long)lo));
+                    gk = lo;                                  // already a key (non-negative f64 bits)
                     gi = int(unsigned(hi & 0xffffffffull));
                     gw = q;
                 }
-#pragma unroll
-                for (int off = 16; off > 0; off >>= 1) {
-                    const T ov = __shfl_down_sync(0xffffffffu, gv, off);
-                    const int oi = __shfl_down_sync(0xffffffffu, gi, off);
-                    const int ow = __shfl_down_sync(0xffffffffu, gw, off);
-                    if (cand_better(ov, oi, gv, gi)) { gv = ov; gi = oi; gw = ow; }
+                {
+                    unsigned wm;
+                    warp_argmax(gk, gi, wm);
+                    gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
                 }
-                if (lane == 0) { red_abs[par][warp] = gv; red_idx[par][warp] = gi; red_win[par][warp] = gw; }
+                if (lane == 0) { red_key[par][warp] = gk; red_idx[par][warp] = gi; red_win[par][warp] = gw; }
                 asm volatile("bar.sync 1, %0;" ::"n"(HUB_ROOT_THREADS) : "memory");
+                TRACE(5);
                 int sing = 0;
                 if (warp == 0) {
-                    gv = (lane < HUB_ROOT_WARPS) ? red_abs[par][lane] : T(-1);
+                    gk = (lane < HUB_ROOT_WARPS) ? red_key[par][lane] : 0ull;
                     gi = (lane < HUB_ROOT_WARPS) ? red_idx[par][lane] : INT_MAX;
                     gw = (lane < HUB_ROOT_WARPS) ? red_win[par][lane] : 0;
-#pragma unroll
-                    for (int off = 4; off > 0; off >>= 1) {
-                        const T ov = __shfl_down_sync(0xffffffffu, gv, off);
-                        const int oi = __shfl_down_sync(0xffffffffu, gi, off);
-                        const int ow = __shfl_down_sync(0xffffffffu, gw, off);
-                        if (cand_better(ov, oi, gv, gi)) { gv = ov; gi = oi; gw = ow; }
-                    }
+                    unsigned wm;
+                    warp_argmax(gk, gi, wm);
+                    gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
                     if (lane == 0) {
+                        const T gv = T(__longlong_as_double((long long)gk));
                         sing = (gv < Eps<T>::v()) ? 1 : 0;         // lu.rs:179-183 (NaN: false, continues)
                         msg_store(sc.result + par, (unsigned long long)(unsigned)gi | ((unsigned long long)(unsigned)gw << 32),
                                   (unsigned long long)sing | ((unsigned long long)tag << 32));
@@ -201,6 +221,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                             ipiv[J + c] = gi;
                         }
                         *((volatile int *)&piv_sm[c]) = sing ? -1 : gi;
+                        if (sc.trace) sc.trace[c * 8 + 6] = gtime();
                     }
                     sing = __shfl_sync(0xffffffffu, sing, 0);
                     if (lane == 0) sh_sing = sing;
@@ -220,8 +241,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         if (warp != HUB_ROOT_WARPS && (t2 < 0 || t2 >= ncols)) return;
         for (int c = 0; c < jb; ++c) {
             int p;
-            while ((p = *((volatile int *)&piv_sm[c])) == INT_MIN) {
-            }
+            while ((p = *((volatile int *)&piv_sm[c])) == INT_MIN) __nanosleep(200);   // never compete with the root warps
             if (p < 0) return;                       // singular
             const int d = J + c;
             if (p == d) continue;
@@ -292,6 +312,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int lo = max(0, d - r0);             // first local row still active
         const bool owns_d = (d >= r0 && d < r1);
 
+        if (b == 0) TRACE(0);
         // ---- local argmax over active rows of column c (first max wins) ----
         T best = T(-1);
         int bidx = INT_MAX;
@@ -299,33 +320,30 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             const T v = fabs(s[r * PLDS + c]);
             if (v > best) { best = v; bidx = r0 + r; }     // NaN: comparison false, never wins
         }
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            const T ov = __shfl_down_sync(0xffffffffu, best, off);
-            const int oi = __shfl_down_sync(0xffffffffu, bidx, off);
-            if (cand_better(ov, oi, best, bidx)) { best = ov; bidx = oi; }
+        unsigned long long bkey = key_of(double(best));
+        if (bkey == 0ull && best < T(0)) bidx = INT_MAX;
+        {
+            unsigned wm;
+            warp_argmax(bkey, bidx, wm);
         }
-        if (lane == 0) { red_abs[0][warp] = best; red_idx[0][warp] = bidx; }
+        if (lane == 0) { red_key[0][warp] = bkey; red_idx[0][warp] = bidx; }
         __syncthreads();
         if (warp == 0) {
-            best = (lane < PANEL_THREADS / 32) ? red_abs[0][lane] : T(-1);
+            bkey = (lane < PANEL_THREADS / 32) ? red_key[0][lane] : 0ull;
             bidx = (lane < PANEL_THREADS / 32) ? red_idx[0][lane] : INT_MAX;
-#pragma unroll
-            for (int off = 8; off > 0; off >>= 1) {
-                const T ov = __shfl_down_sync(0xffffffffu, best, off);
-                const int oi = __shfl_down_sync(0xffffffffu, bidx, off);
-                if (cand_better(ov, oi, best, bidx)) { best = ov; bidx = oi; }
-            }
+            unsigned wm;
+            warp_argmax(bkey, bidx, wm);
             if (lane == 0) {
                 // reference starts the scan with curr_max = a_dd even when it is NaN (lu.rs:170-171):
                 // then no later row can win.  Post +inf for that row so it wins the global reduce.
                 if (owns_d) {
                     const T dv = s[(d - r0) * PLDS + c];
-                    if (dv != dv) { best = inf_of(T(0)); bidx = d; }
+                    if (dv != dv) { bkey = key_of(CUDART_INF); bidx = d; }
                 }
                 sh_idx = bidx;
                 // candidate packet first: it is what the hub is waiting for
-                msg_store(sc.packets + par * GMAX + b, bits_of(double(best)), (unsigned long long)(unsigned)bidx | tag_hi);
+                msg_store(sc.packets + par * GMAX + b, bkey, (unsigned long long)(unsigned)bidx | tag_hi);
+                if (b == 0 && sc.trace) sc.trace[c * 8 + 1] = gtime();
             }
         }
         __syncthreads();
@@ -352,6 +370,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             }
         }
         __syncthreads();
+        if (b == 0) TRACE(2);
         const int prow_idx = sh_idx, win = sh_win;
         if (sh_sing) return;                       // uniform across the grid; the hub set *info
         if ((tid & ~31) < jb) {                   // whole warps poll (lanes past jb re-read chunk jb-1)
@@ -379,19 +398,31 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             }
             __syncthreads();
         }
+        if (b == 0) TRACE(3);
         // ---- multipliers (one IEEE division per row), then rank-1 update with mul, sub ----
         const T piv = prow_s[c];
         const int lo2 = max(0, d + 1 - r0);
         for (int r = lo2 + tid; r < nrows; r += PANEL_THREADS) s[r * PLDS + c] = div_rn(s[r * PLDS + c], piv);
         __syncthreads();
         if (c + 1 < jb) {
-            for (int r = lo2 + warp; r < nrows; r += PANEL_THREADS / 32) {
-                const T m = s[r * PLDS + c];
-                for (int cc = c + 1 + lane; cc < jb; cc += 32)
-                    s[r * PLDS + cc] = sub_rn(s[r * PLDS + cc], mul_rn(m, prow_s[cc]));
+            // rank-1 update, four rows in flight per warp (independent mul/sub chains)
+            constexpr int NW = PANEL_THREADS / 32;
+            for (int rb = lo2 + warp; rb < nrows; rb += 4 * NW) {
+                T m[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) m[u] = (rb + u * NW < nrows) ? s[(rb + u * NW) * PLDS + c] : T(0);
+                for (int cc = c + 1 + lane; cc < jb; cc += 32) {
+                    const T pv = prow_s[cc];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + u * NW;
+                        if (r < nrows) s[r * PLDS + cc] = sub_rn(s[r * PLDS + cc], mul_rn(m[u], pv));
+                    }
+                }
             }
         }
         __syncthreads();
+        if (b == 0) TRACE(4);
     }
 
     for (int idx = tid; idx < nrows * jb; idx += PANEL_THREADS) {
@@ -604,6 +635,7 @@ int gemm_update<float>(size_t m, size_t k, size_t n, const float *a, size_t lda,
 }
 
 int g_num_sms = 0;
+unsigned long long *g_lu_trace = nullptr;
 int g_lu_gmax_ref();
 int g_lu_dbg_ref();
 
@@ -656,6 +688,7 @@ PanelScratch scratch_view(LuWorkspace &ws) {
     sc.plan = reinterpret_cast<LaswpPlan *>(sp + SC_PLAN);
     sc.state = reinterpret_cast<PlanState *>(sp + SC_STATE);
     sc.rowid = nullptr;
+    sc.trace = nullptr;
     return sc;
 }
 
@@ -672,6 +705,12 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
     }
     PanelScratch sc = scratch_view(ws);
     sc.plan = plan;
+    if (g_lu_dbg_ref() & 8) {
+        static unsigned long long *trace = nullptr;
+        if (!trace) RLA_CUDA(cudaMalloc(&trace, 64 * 8 * sizeof(unsigned long long)));
+        sc.trace = trace;
+        g_lu_trace = trace;
+    }
     for (int j = J0; j < J0 + w; j += PW) {
         const int jb = min(PW, J0 + w - j);
         const int nrem = n - j;
@@ -750,6 +789,11 @@ int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bi
 namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } }
 
 size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
+int lu_trace_fetch(unsigned long long *host512) {
+    if (!g_lu_trace) return RLA_ERR_INVALID;
+    RLA_CUDA(cudaMemcpy(host512, g_lu_trace, 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    return RLA_OK;
+}
 
 template <typename T>
 int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
