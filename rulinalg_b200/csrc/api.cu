@@ -63,12 +63,10 @@ struct Context {
     cudaStream_t copy_in = nullptr;      // H2D
     cudaStream_t copy_out = nullptr;     // D2H
     Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync;
-    Buffer hStage[2];                    // pinned bounce buffers for pageable operands
     Buffer hSmall;                       // pinned scalars (info, perm)
     LuWorkspace lu_ws;
     std::vector<cudaEvent_t> events;
     Context() {
-        hStage[0].pinned_host = hStage[1].pinned_host = true;
         hSmall.pinned_host = true;
     }
 };
@@ -112,12 +110,6 @@ int ensure_ctx(int device = -1) {
 }
 
 cudaStream_t pick_stream(void *s) { return static_cast<cudaStream_t>(s); }   // NULL = CUDA legacy default stream
-
-bool is_pinned(const void *p) {
-    cudaPointerAttributes at;
-    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
-    return at.type == cudaMemoryTypeHost;
-}
 
 // Row-strided host matrix -> contiguous-ish device matrix (ld elements per row).
 template <typename T>

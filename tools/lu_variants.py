@@ -15,9 +15,9 @@ def run(n, reps=3):
         e0.record(); rla.check(l.rla_dgetrf_dev(n, a.data_ptr(), n, perm.data_ptr(), info.data_ptr(), s)); e1.record(); e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for n in (1024, 4096, 8192, 16384, 32768):
-    for dbg in (0, 4):
-        for gmax in (147,):
+for n in (16384, 32768):
+    for dbg in (0,):
+        for gmax in (147, 128, 112, 96, 84, 64):
             l.rla_set_tuning(b"lu_gmax", gmax); l.rla_set_tuning(b"lu_dbg", dbg)
             try:
                 ms = run(n)
