@@ -86,6 +86,13 @@ RLA_API int rla_sgetrs(size_t n, const float *lu, const size_t *perm, float *b);
 RLA_API int rla_dgetri(size_t n, const double *lu, const size_t *perm, double *inv);
 RLA_API int rla_sgetri(size_t n, const float *lu, const size_t *perm, float *inv);
 
+/* solve_l_triangular / solve_u_triangular (src/matrix/base/mod.rs:1015-1067 -> forward_substitution /
+ * back_substitution, src/matrix/mod.rs:318-398) -- SURVEY 8f.  `a` is n x n row-major with row stride rs (only the
+ * lower / upper triangle incl. the diagonal is read); x holds y on entry and the solution on exit.
+ * RLA_ERR_SINGULAR when some |a_ii| < epsilon (x is then left untouched). */
+RLA_API int rla_dtrsv(int lower, size_t n, const double *a, ptrdiff_t rs, double *x);
+RLA_API int rla_strsv(int lower, size_t n, const float *a, ptrdiff_t rs, float *x);
+
 /* Factorisation kept resident in HBM for repeated solves (PartialPivLu is built for "multiple
  * such linear systems involving the same A", lu.rs:203-206).  rla_dgetrf_keep = rla_dgetrf
  * that also returns a handle; rla_lu_solve = rla_dgetrs without re-uploading lu. */

@@ -354,6 +354,31 @@ int getrs_host(size_t n, const T *lu, const size_t *perm, T *b) {
 }
 
 template <typename T>
+int trsv_host(int lower, size_t n, const T *a, ptrdiff_t rs, T *x) {
+    if (n == 0) return RLA_OK;
+    if (!a || !x || rs < ptrdiff_t(n)) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dVec.ensure(n * sizeof(T)));
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.dSync.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    T *dA = static_cast<T *>(cx.dA.p), *dX = static_cast<T *>(cx.dVec.p);
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p), *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    RLA_TRY(upload_matrix(dA, ld, a, size_t(rs), n, n, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(dX, x, n * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(trsv_launch<T>(lower != 0, n, dA, ld, dX, dInfo, static_cast<int32_t *>(cx.dSync.p), cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*hInfo != 0) return RLA_ERR_SINGULAR;
+    RLA_CUDA(cudaMemcpyAsync(x, dX, n * sizeof(T), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
+template <typename T>
 int getri_host(size_t n, const T *lu, const size_t *perm, T *inv) {
     if (n == 0) return RLA_OK;
     if (!lu || !perm || !inv) return RLA_ERR_INVALID;
@@ -422,6 +447,9 @@ int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
     RLA_TRY(ensure_ctx());
     return getri_launch<float>(n, lu, ld, d_perm, x, ldx, d_info, pick_stream(stream));
 }
+
+int rla_dtrsv(int lower, size_t n, const double *a, ptrdiff_t rs, double *x) { return trsv_host<double>(lower, n, a, rs, x); }
+int rla_strsv(int lower, size_t n, const float *a, ptrdiff_t rs, float *x) { return trsv_host<float>(lower, n, a, rs, x); }
 
 int rla_dgetrf_keep(size_t n, double *lu, size_t *perm, rla_lu_handle **out) {
     if (!out) return RLA_ERR_INVALID;

@@ -123,7 +123,7 @@ template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
 // sync words: [0] ticket, [1] done
-template <typename T, bool LOWER>
+template <typename T, bool LOWER, bool UNIT = LOWER>
 __global__ void __launch_bounds__(TRSV_THREADS, 2)
 trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int32_t *__restrict__ info) {
     using V2 = typename Vec2<T>::type;
@@ -212,8 +212,20 @@ trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int
         T va = (row0 + ra < n) ? sub_rn(__ldcg(x + row0 + ra), rsum[ra]) : T(0);
         T vb = (row0 + rb < n) ? sub_rn(__ldcg(x + row0 + rb), rsum[rb]) : T(0);
         if (LOWER) {
+            T ia = T(1), ib = T(1);
+            if (!UNIT) {
+                // forward_substitution (src/matrix/mod.rs:363-398): |l_ii| < eps -> DivByZero, then divide
+                const T da = diag[ra * (TB + 1) + ra], db = diag[rb * (TB + 1) + rb];
+                if (row0 + ra < n && fabs(da) < EpsS<T>::v()) atomicCAS(info, 0, row0 + ra + 1);
+                if (row0 + rb < n && fabs(db) < EpsS<T>::v()) atomicCAS(info, 0, row0 + rb + 1);
+                ia = div_rn(T(1), da);
+                ib = div_rn(T(1), db);
+            }
 #pragma unroll 8
             for (int k = 0; k < TB; ++k) {
+                if (!UNIT && lane == (k & 31)) {
+                    if (k < 32) va *= ia; else vb *= ib;
+                }
                 const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
                 if (ra > k) va -= diag[ra * (TB + 1) + k] * xk;
                 if (rb > k) vb -= diag[rb * (TB + 1) + k] * xk;
@@ -281,6 +293,27 @@ int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *
 }
 template int getri_small_launch<double>(int, const double *, size_t, const int64_t *, double *, size_t, int32_t *, cudaStream_t);
 template int getri_small_launch<float>(int, const float *, size_t, const int64_t *, float *, size_t, int32_t *, cudaStream_t);
+
+// solve_l_triangular / solve_u_triangular (src/matrix/base/mod.rs:1015-1067 -> forward_/back_substitution,
+// src/matrix/mod.rs:318-398): triangular part of a general matrix, diagonal included, |diag| < eps -> DivByZero.
+// d_x holds y on entry, x on exit (unspecified when *d_info != 0).
+template <typename T>
+int trsv_launch(bool lower, size_t n_, const T *a, size_t ld, T *d_x, int32_t *d_info, int32_t *d_sync, cudaStream_t st) {
+    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    if (n == 0) return RLA_OK;
+    const int nblk = (n + TB - 1) / TB;
+    RLA_CUDA(cudaMemsetAsync(d_sync, 0, 4 * sizeof(int32_t), st));
+    if (lower)
+        trsv_kernel<T, true, false><<<nblk, TRSV_THREADS, 0, st>>>(n, a, ld, d_x, d_sync, d_info);
+    else
+        trsv_kernel<T, false, false><<<nblk, TRSV_THREADS, 0, st>>>(n, a, ld, d_x, d_sync, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+template int trsv_launch<double>(bool, size_t, const double *, size_t, double *, int32_t *, int32_t *, cudaStream_t);
+template int trsv_launch<float>(bool, size_t, const float *, size_t, float *, int32_t *, int32_t *, cudaStream_t);
 
 template int getrs_launch<double>(size_t, const double *, size_t, const int64_t *, double *, double *, int32_t *,
                                   int32_t *, cudaStream_t);

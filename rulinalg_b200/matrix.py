@@ -121,6 +121,26 @@ class _BaseMatrix:
         _lib.check(st)
         return Matrix._from_array(new_data)
 
+    # ---- solve_u_triangular / solve_l_triangular (base/mod.rs:1015-1067) ---------------------------
+    def _tri_solve(self, y: "Vector", lower: bool) -> "Vector":
+        if self.cols() != y.size():
+            raise Panic(f"Vector size {y.size()} != {self.cols()} Matrix column count.")
+        if self.rows() != self.cols():
+            raise Panic("Matrix U must be square." if not lower else "Matrix L must be square.")
+        n = self.rows()
+        x = np.array(y.data(), dtype=self._arr.dtype, copy=True)
+        pre = _dtype_pre(self._arr.dtype)
+        st = getattr(_lib.lib(), f"rla_{pre}trsv")(1 if lower else 0, n, self.as_ptr(), self.row_stride(), x.ctypes.data)
+        if _lib.check(st) == _lib.RLA_ERR_SINGULAR:
+            raise Error(ErrorKind.DivByZero, _TRI_SINGULAR_MSG)
+        return Vector(x)
+
+    def solve_u_triangular(self, y: "Vector") -> "Vector":
+        return self._tri_solve(y, lower=False)
+
+    def solve_l_triangular(self, y: "Vector") -> "Vector":
+        return self._tri_solve(y, lower=True)
+
     def sub_slice(self, start, rows, cols):
         return MatrixSlice.from_matrix(self, start, rows, cols)
 

@@ -456,6 +456,44 @@ def test_inverse_singular_is_div_by_zero(rla):
         rla.Matrix.ones(2, 3).inverse()
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_triangular_solves(rla, oracle, dtype):
+    # solve_u_triangular / solve_l_triangular (base/mod.rs:1015-1067; tests/mat/mod.rs:28-39; benches/linalg/triangular.rs)
+    for fn in ("solve_l_triangular", "solve_u_triangular"):
+        with pytest.raises(rla.Error) as ei:
+            getattr(M(rla, [[0.0]], dtype), fn)(rla.Vector(np.array([1.0], dtype)))
+        assert ei.value.kind() == rla.ErrorKind.DivByZero
+    x = M(rla, [[1.0, 0.0], [2.0, 1.0]], dtype).solve_l_triangular(rla.Vector(np.array([1.0, 3.0], dtype)))
+    assert x.data().tolist() == [1.0, 1.0]
+    with pytest.raises(rla.Panic):
+        M(rla, [[1.0, 0.0], [2.0, 1.0]], dtype).solve_u_triangular(rla.Vector(np.array([1.0], dtype)))
+    u = U(dtype)
+    for n in (5, 64, 65, 300, 1000):
+        a = oracle.fill_uniform((n, n), 31, dtype, lo=-1.0, scale=2.0)
+        a[np.arange(n), np.arange(n)] = 2.0 + np.arange(n) % 3          # well-conditioned triangles
+        a = (a / np.sqrt(n)).astype(dtype)
+        a[np.arange(n), np.arange(n)] *= np.sqrt(n).astype(dtype)
+        y = oracle.fill_uniform((n,), 32, dtype)
+        xl = rla.Matrix.from_numpy(a).solve_l_triangular(rla.Vector(y)).data().astype(np.float64)
+        xu = rla.Matrix.from_numpy(a).solve_u_triangular(rla.Vector(y)).data().astype(np.float64)
+        rl = oracle.forward_substitution(np.tril(a), y).astype(np.float64)
+        ru = oracle.back_substitution(np.triu(a), y).astype(np.float64)
+        tol = 64 * n * u
+        assert np.max(np.abs(xl - rl)) <= tol * np.max(np.abs(rl)), (fn, n)
+        assert np.max(np.abs(xu - ru)) <= tol * np.max(np.abs(ru)), (fn, n)
+    # identity of order 10000 (benches/linalg/triangular.rs:6-58) and a strided slice operand
+    n = 2000
+    eye = rla.Matrix.identity(n, dtype)
+    y = oracle.fill_uniform((n,), 33, dtype)
+    assert np.array_equal(eye.solve_u_triangular(rla.Vector(y)).data(), y)
+    assert np.array_equal(eye.solve_l_triangular(rla.Vector(y)).data(), y)
+    big = rla.Matrix.from_numpy(np.pad(np.triu(np.ones((100, 100), dtype)) + 99 * np.eye(100, dtype=dtype), ((3, 0), (5, 2))))
+    sl = rla.MatrixSlice.from_matrix(big, [3, 5], 100, 100)
+    xs = sl.solve_u_triangular(rla.Vector(np.ones(100, dtype))).data()
+    ref = oracle.back_substitution(np.ascontiguousarray(sl._arr), np.ones(100, dtype))
+    assert np.max(np.abs(xs.astype(np.float64) - ref)) <= 64 * 100 * u
+
+
 def test_launch_counter_and_version(rla):
     l = rla.lib()
     l.rla_launch_count_reset()
