@@ -17,6 +17,7 @@ namespace rla {
 extern int g_dgemm_cfg;   // dgemm.cu
 extern int g_lu_gmax, g_lu_dbg;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
+int g_host_gemm_s = 4;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline
 
 namespace {
 
@@ -191,7 +192,7 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         // [0..s-1] x s) and downloads it.  Work availability grows quadratically while uploads proceed linearly,
         // so the kernel starts after 2/S of the H2D traffic instead of after all of B, and PCIe in both
         // directions stays busy under the DMMA kernel.
-        const size_t S = 8;
+        const size_t S = size_t(g_host_gemm_s);
         const size_t pm = ((m + S - 1) / S + 127) / 128 * 128, pn = ((n + S - 1) / S + 127) / 128 * 128;
         const size_t sm = (m + pm - 1) / pm, sn = (n + pn - 1) / pn;
         const size_t steps = sm > sn ? sm : sn;
@@ -610,6 +611,11 @@ int rla_set_tuning(const char *key, int value) {
     if (strcmp(key, "lu_gmax") == 0) {
         if (value < 1) return RLA_ERR_INVALID;
         g_lu_gmax = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "host_gemm_s") == 0) {
+        if (value < 1 || value > 64) return RLA_ERR_INVALID;
+        g_host_gemm_s = value;
         return RLA_OK;
     }
     if (strcmp(key, "host_gemm_2d") == 0) {
