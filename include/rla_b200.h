@@ -93,6 +93,12 @@ RLA_API int rla_sgetri(size_t n, const float *lu, const size_t *perm, float *inv
 RLA_API int rla_dtrsv(int lower, size_t n, const double *a, ptrdiff_t rs, double *x);
 RLA_API int rla_strsv(int lower, size_t n, const float *a, ptrdiff_t rs, float *x);
 
+/* `&Matrix * &Vector` (src/matrix/impl_ops.rs:298-314) -- SURVEY 8f.  y (length m) = A (m x n, row stride rs) * x. */
+RLA_API int rla_dgemv(size_t m, size_t n, const double *a, ptrdiff_t rs, const double *x, double *y);
+RLA_API int rla_sgemv(size_t m, size_t n, const float *a, ptrdiff_t rs, const float *x, float *y);
+RLA_API int rla_dgemv_dev(size_t m, size_t n, const double *a, size_t lda, const double *x, double *y, void *stream);
+RLA_API int rla_sgemv_dev(size_t m, size_t n, const float *a, size_t lda, const float *x, float *y, void *stream);
+
 /* Factorisation kept resident in HBM for repeated solves (PartialPivLu is built for "multiple
  * such linear systems involving the same A", lu.rs:203-206).  rla_dgetrf_keep = rla_dgetrf
  * that also returns a handle; rla_lu_solve = rla_dgetrs without re-uploading lu. */

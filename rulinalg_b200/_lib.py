@@ -18,7 +18,7 @@ RLA_ERR_NO_DEVICE = -3
 # every symbol include/rla_b200.h declares (tests/test_abi.py checks the .so exports all of them)
 SYMBOLS = [
     "rla_dgemm", "rla_sgemm", "rla_dgetrf", "rla_sgetrf", "rla_dgetrs", "rla_sgetrs",
-    "rla_dtrsv", "rla_strsv", "rla_dgetri", "rla_sgetri", "rla_dgetri_dev", "rla_sgetri_dev",
+    "rla_dgemv", "rla_sgemv", "rla_dgemv_dev", "rla_sgemv_dev", "rla_dtrsv", "rla_strsv", "rla_dgetri", "rla_sgetri", "rla_dgetri_dev", "rla_sgetri_dev",
     "rla_dgetrf_keep", "rla_dlu_solve", "rla_lu_free",
     "rla_init", "rla_device_count", "rla_dev_alloc", "rla_dev_free", "rla_host_alloc_pinned",
     "rla_host_free_pinned", "rla_memcpy_h2d", "rla_memcpy_d2h", "rla_stream_sync",
@@ -55,6 +55,10 @@ def lib():
         getattr(l, f).argtypes = [sz, P, P]
     for f in ("rla_dgetrs", "rla_sgetrs"):
         getattr(l, f).argtypes = [sz, P, P, P]
+    for f in ("rla_dgemv", "rla_sgemv"):
+        getattr(l, f).argtypes = [sz, sz, P, pd, P, P]
+    for f in ("rla_dgemv_dev", "rla_sgemv_dev"):
+        getattr(l, f).argtypes = [sz, sz, P, sz, P, P, P]
     for f in ("rla_dtrsv", "rla_strsv"):
         getattr(l, f).argtypes = [i32, sz, P, pd, P]
     for f in ("rla_dgetri", "rla_sgetri"):

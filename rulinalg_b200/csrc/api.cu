@@ -355,6 +355,25 @@ int getrs_host(size_t n, const T *lu, const size_t *perm, T *b) {
 }
 
 template <typename T>
+int gemv_host(size_t m, size_t n, const T *a, ptrdiff_t rs, const T *x, T *y) {
+    if (m == 0) return RLA_OK;
+    if (!y || (n > 0 && (!a || !x)) || rs < ptrdiff_t(n)) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n ? n : 1, sizeof(T));
+    RLA_TRY(cx.dA.ensure(m * ld * sizeof(T)));
+    RLA_TRY(cx.dVec.ensure((n ? n : 1) * sizeof(T)));
+    RLA_TRY(cx.dVec2.ensure(m * sizeof(T)));
+    T *dA = static_cast<T *>(cx.dA.p), *dX = static_cast<T *>(cx.dVec.p), *dY = static_cast<T *>(cx.dVec2.p);
+    RLA_TRY(upload_matrix(dA, ld, a, size_t(rs), m, n, cx.stream));
+    if (n) RLA_CUDA(cudaMemcpyAsync(dX, x, n * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(gemv_launch<T>(m, n, dA, ld, dX, dY, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(y, dY, m * sizeof(T), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
+template <typename T>
 int trsv_host(int lower, size_t n, const T *a, ptrdiff_t rs, T *x) {
     if (n == 0) return RLA_OK;
     if (!a || !x || rs < ptrdiff_t(n)) return RLA_ERR_INVALID;
@@ -449,6 +468,16 @@ int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
     return getri_launch<float>(n, lu, ld, d_perm, x, ldx, d_info, pick_stream(stream));
 }
 
+int rla_dgemv(size_t m, size_t n, const double *a, ptrdiff_t rs, const double *x, double *y) { return gemv_host<double>(m, n, a, rs, x, y); }
+int rla_sgemv(size_t m, size_t n, const float *a, ptrdiff_t rs, const float *x, float *y) { return gemv_host<float>(m, n, a, rs, x, y); }
+int rla_dgemv_dev(size_t m, size_t n, const double *a, size_t lda, const double *x, double *y, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return gemv_launch<double>(m, n, a, lda, x, y, pick_stream(stream));
+}
+int rla_sgemv_dev(size_t m, size_t n, const float *a, size_t lda, const float *x, float *y, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return gemv_launch<float>(m, n, a, lda, x, y, pick_stream(stream));
+}
 int rla_dtrsv(int lower, size_t n, const double *a, ptrdiff_t rs, double *x) { return trsv_host<double>(lower, n, a, rs, x); }
 int rla_strsv(int lower, size_t n, const float *a, ptrdiff_t rs, float *x) { return trsv_host<float>(lower, n, a, rs, x); }
 

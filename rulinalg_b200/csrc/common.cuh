@@ -69,6 +69,8 @@ int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *
                        cudaStream_t st);
 template <typename T>
 int trsv_launch(bool lower, size_t n, const T *a, size_t ld, T *d_x, int32_t *d_info, int32_t *d_sync, cudaStream_t st);
+template <typename T>
+int gemv_launch(size_t m, size_t n, const T *a, size_t lda, const T *x, T *y, cudaStream_t st);
 size_t lu_plan_bytes();
 int lu_trace_fetch(unsigned long long *host512);
 template <typename T>

@@ -105,7 +105,14 @@ class _BaseMatrix:
         if isinstance(m, (int, float)):
             return Matrix._from_array(self._arr * self._arr.dtype.type(m))
         if isinstance(m, Vector):
-            raise NotImplementedError("Matrix * Vector (impl_ops.rs:298-314) is outside the B200 hot path")
+            # &Matrix * &Vector (impl_ops.rs:298-314) -> rla_?gemv
+            if m.size() != self.cols():
+                raise Panic("Matrix and Vector dimensions do not agree.")
+            xin = np.ascontiguousarray(m.data(), dtype=self._arr.dtype)
+            out = np.empty(self.rows(), dtype=self._arr.dtype)
+            fnv = getattr(_lib.lib(), f"rla_{_dtype_pre(self._arr.dtype)}gemv")
+            _lib.check(fnv(self.rows(), self.cols(), self.as_ptr(), self.row_stride(), xin.ctypes.data, out.ctypes.data))
+            return Vector(out)
         if not isinstance(m, _BaseMatrix):
             return NotImplemented
         if self.cols() != m.rows():

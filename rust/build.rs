@@ -10,7 +10,7 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(env::var("RLA_B200_CSRC").unwrap_or_else(|_| "rla_b200/csrc".into()));
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
-    let srcs = ["api.cu", "dgemm.cu", "sgemm.cu", "lu.cu", "solve.cu", "fill.cu"];
+    let srcs = ["api.cu", "dgemm.cu", "sgemm.cu", "lu.cu", "solve.cu", "fill.cu", "gemv.cu"];
     let mut objs = Vec::new();
     for s in srcs.iter() {
         let obj = out.join(format!("{}.o", s));

@@ -127,7 +127,7 @@ def test_mul_dimension_mismatch_panics(rla):
 
 
 SHAPES = [(1, 1, 1), (3, 2, 3), (17, 5, 9), (64, 64, 64), (128, 128, 128), (129, 130, 131), (200, 333, 77),
-          (255, 1000, 257), (512, 512, 512), (1024, 1024, 1024), (4096, 256, 256)]
+          (255, 1000, 257), (512, 512, 512), (1024, 1024, 1024), (4096, 256, 256), (65536, 256, 256)]
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
@@ -492,6 +492,55 @@ def test_triangular_solves(rla, oracle, dtype):
     xs = sl.solve_u_triangular(rla.Vector(np.ones(100, dtype))).data()
     ref = oracle.back_substitution(np.ascontiguousarray(sl._arr), np.ones(100, dtype))
     assert np.max(np.abs(xs.astype(np.float64) - ref)) <= 64 * 100 * u
+
+
+def test_lu_solve_device_resident_large_property(rla):
+    # BASELINE C5-sized path on one GPU through size-independent properties (no CPU oracle at this size):
+    # device-resident decompose + solve of A x = A*1 must return ones; |l_ij| <= 1; perm is a permutation.
+    import torch
+    n = 16384
+    l = rla.lib()
+    torch.cuda.set_device(0)
+    s = torch.cuda.current_stream().cuda_stream
+    a0 = torch.empty(n, n, dtype=torch.float64, device="cuda")
+    assert l.rla_fill_uniform_f64_dev(a0.data_ptr(), n, n, n, 12, 0, 0.0, 1.0, s) == 0
+    b = a0 @ torch.ones(n, dtype=torch.float64, device="cuda")          # checker-side product (torch), not the product path
+    lu = a0.clone()
+    perm = torch.empty(n, dtype=torch.int64, device="cuda")
+    info = torch.ones(1, dtype=torch.int32, device="cuda")
+    assert l.rla_dgetrf_dev(n, lu.data_ptr(), n, perm.data_ptr(), info.data_ptr(), s) == 0
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    assert torch.equal(torch.sort(perm).values, torch.arange(n, device="cuda"))
+    assert float(torch.tril(lu, -1).abs().max().item()) <= 1.0
+    x = b.clone()
+    assert l.rla_dgetrs_dev(n, lu.data_ptr(), n, perm.data_ptr(), x.data_ptr(), info.data_ptr(), s) == 0
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    err = float((x - 1.0).abs().max().item())
+    resid = float((a0 @ x - b).abs().max().item()) / (float(a0.abs().sum(dim=1).max().item()) * float(x.abs().max().item()) * n * 2.0 ** -52)
+    assert resid <= 16, resid
+    assert err <= 1e-5, err
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_matrix_vector_product(rla, oracle, dtype):
+    # &Matrix * &Vector (impl_ops.rs:298-314): row-wise utils::dot in the reference
+    a = M(rla, [[1, 2, 3], [4, 5, 6]], dtype)
+    assert (a * rla.Vector(np.array([1, 2, 3], dtype))).data().tolist() == [14.0, 32.0]
+    with pytest.raises(rla.Panic, match="Matrix and Vector dimensions do not agree."):
+        a * rla.Vector(np.array([1, 2], dtype))
+    u = U(dtype)
+    for (m, n) in ((1, 1), (7, 5), (300, 1000), (1000, 301), (2048, 4096)):
+        an = oracle.fill_uniform((m, n), 41, dtype, lo=-1.0, scale=2.0)
+        xn = oracle.fill_uniform((n,), 42, dtype, lo=-1.0, scale=2.0)
+        got = (rla.Matrix.from_numpy(an) * rla.Vector(xn)).data().astype(np.float64)
+        ref = np.array([oracle.dot(an[i], xn) for i in range(min(m, 64))], dtype=np.float64)
+        bound = 2 * gamma(n, dtype) * (np.abs(an.astype(np.float64)) @ np.abs(xn.astype(np.float64)))
+        assert np.all(np.abs(got[:len(ref)] - ref) <= bound[:len(ref)] + 0.0)
+        assert np.all(np.abs(got - an.astype(np.float64) @ xn.astype(np.float64)) <= bound)
+    assert (rla.Matrix.zeros(0, 3, dtype) * rla.Vector(np.zeros(3, dtype))).size() == 0
+    assert np.all((rla.Matrix.zeros(2, 0, dtype) * rla.Vector(np.zeros(0, dtype))).data() == 0)
 
 
 def test_launch_counter_and_version(rla):

@@ -55,6 +55,12 @@ def main():
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
                 del a, b, c
+    if "gemv" in which:
+        for n in (4096, 16384, 32768):
+            a = torch.rand(n, n, dtype=torch.float64, device="cuda"); x = torch.rand(n, dtype=torch.float64, device="cuda"); y = torch.empty(n, dtype=torch.float64, device="cuda")
+            best, med = timed(lambda: rla.check(l.rla_dgemv_dev(n, n, a.data_ptr(), n, x.data_ptr(), y.data_ptr(), s)), 10)
+            print(json.dumps(dict(op="dgemv", n=n, ms=best, gbs=8 * n * n / best * 1e-6)), flush=True)
+            del a
     if "pcie" in which:
         nbytes = 1 << 30
         h = torch.empty(nbytes, dtype=torch.uint8).pin_memory()
