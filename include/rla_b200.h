@@ -183,8 +183,8 @@ RLA_API int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size
 RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
                              uint64_t offset, float lo, float scale, void *stream);
 
-/* Tuning knobs (development / benchmarking).  "dgemm_cfg": -1 = auto (default), 0 = 128x64 CTA tile with
- * two CTAs per SM, 1 = 128x128 CTA tile with one CTA per SM.  "lu_gmax": cap on the panel kernel's row
+/* Tuning knobs (development / benchmarking).  "dgemm_cfg": -1 = auto (default), 0..6 = a fixed CTA shape
+ * (see csrc/dgemm.cu).  "lu_gmax": cap on the panel kernel's row
  * CTAs.  "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
 RLA_API int rla_set_tuning(const char *key, int value);
 

@@ -11,6 +11,9 @@
 //            slab barrier, issues its cp.async or runs its epilogue, the other keeps the DMMA pipe fed.
 //     cfg 1  128x128 tile, 8 warps (2x4), 4-stage ring, one CTA per SM.
 //     cfg 2  as cfg 1 with k-slab 32 and a 3-stage ring (half the barriers; +0.4 % on long-k products).
+//     cfg 5/6 128x128 tile, 16 warps (4x4) with 32x32 warp tiles (4 warps per scheduler, 120 registers), k-slab
+//            16 / 32.  cfg 6 is the fastest long-k shape by a small margin (34.5 vs 34.3 TFLOP/s at n = 8192):
+//            every tiling lands at 92-93 % of the DMMA issue peak.
 //   A (k contiguous) and B (n contiguous) k-slabs of 16 are staged global->shared with 16-byte
 //   cp.async (LDGSTS), one __syncthreads per slab; the copies for slab kt+S-1 are issued AFTER the
 //   first quarter of slab kt's DMMAs so the tensor pipe never waits on address arithmetic.  Source
@@ -41,13 +44,16 @@ struct Cfg {
     static constexpr size_t SMEM = size_t(STAGES) * (A_STAGE + B_STAGE) * sizeof(double);
     static constexpr int A_CHUNKS = BM * (BK / 2) / THREADS;       // 16-byte chunks per thread per slab
     static constexpr int B_CHUNKS = BK * (BN / 2) / THREADS;
-    static_assert(BM == WM * 64 && BN == WN * 32, "warp tile is 64x32");
+    static constexpr int MT = BM / WM / 8, NT = BN / WN / 8;   // 8x8 DMMA fragments per warp tile (8x4 = 64x32 or 4x4 = 32x32)
+    static_assert(BM == WM * MT * 8 && BN == WN * NT * 8 && MT * NT <= 32, "warp tile");
     static_assert(A_CHUNKS * THREADS == BM * (BK / 2) && B_CHUNKS * THREADS == BK * (BN / 2), "chunking");
 };
 using CfgSmall = Cfg<128, 64, 2, 2, 3, 2>;
 using CfgLarge = Cfg<128, 128, 2, 4, 4, 1>;
 using CfgLargeK32 = Cfg<128, 128, 2, 4, 3, 1, 32>;
 using CfgSmallK32 = Cfg<128, 64, 2, 2, 2, 2, 32>;
+using CfgW16 = Cfg<128, 128, 4, 4, 4, 1, 16>;       // 16 warps, 32x32 warp tiles: 4 warps per scheduler
+using CfgW16K32 = Cfg<128, 128, 4, 4, 3, 1, 32>;
 
 // Per-thread copy plan for the aligned (16-byte) path.  Thread `tid` always copies chunk column
 // `tid % chunks_per_row` of rows `tid / chunks_per_row + i * rows_per_pass`: one base pointer per
@@ -110,16 +116,16 @@ __device__ __forceinline__ void issue_slab(const CopyPlan<C> &p, uint32_t as_bas
 }
 
 template <class C>
-__device__ __forceinline__ void mma_k4(double (&acc)[8][4][2], const double *ap, const double *bp, int kk) {
-    double af[8], bf[4];
+__device__ __forceinline__ void mma_k4(double (&acc)[C::MT][C::NT][2], const double *ap, const double *bp, int kk) {
+    double af[C::MT], bf[C::NT];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) af[i] = ap[i * 8 * C::LDAS + kk];
+    for (int i = 0; i < C::MT; ++i) af[i] = ap[i * 8 * C::LDAS + kk];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) bf[j] = bp[kk * C::LDBS + j * 8];
+    for (int j = 0; j < C::NT; ++j) bf[j] = bp[kk * C::LDBS + j * 8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < C::MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+        for (int j = 0; j < C::NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
 }
 
 template <class C, bool ALIGNED>
@@ -167,11 +173,11 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
         plan.b_src = B + size_t(brow) * ldb + (gn < N ? gn : 0);
     }
 
-    double acc[8][4][2];
+    double acc[C::MT][C::NT][2];
 #pragma unroll
-    for (int i = 0; i < 8; ++i)
+    for (int i = 0; i < C::MT; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int j = 0; j < C::NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
     const int KT = (K + C::BK - 1) / C::BK;
     const int KT_FULL = K / C::BK;                  // slabs needing no k-bound checks
@@ -185,8 +191,8 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
         cp_async_commit();
     }
 
-    const double *a_frag_base = As + (wm * 64 + g) * C::LDAS + t;
-    const double *b_frag_base = Bs + t * C::LDBS + wn * 32 + g;
+    const double *a_frag_base = As + (wm * C::MT * 8 + g) * C::LDAS + t;
+    const double *b_frag_base = Bs + t * C::LDBS + wn * C::NT * 8 + g;
 
     int stage = 0;
     for (int kt = 0; kt < KT; ++kt) {
@@ -214,28 +220,28 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
     // epilogue: thread owns C[row g][cols 2t,2t+1] of each 8x8 fragment
     const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cmat) & 15) == 0);
     const bool interior = vec_ok && (m0 + C::BM <= M) && (n0 + C::BN <= N);
-    double *cbase = Cmat + size_t(m0 + wm * 64 + g) * ldc + n0 + wn * 32 + 2 * t;
+    double *cbase = Cmat + size_t(m0 + wm * C::MT * 8 + g) * ldc + n0 + wn * C::NT * 8 + 2 * t;
     if (interior) {
         if (beta == 0.0) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < C::MT; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < C::NT; ++j)
                     *reinterpret_cast<double2 *>(cbase + size_t(i * 8) * ldc + j * 8) =
                         make_double2(alpha * acc[i][j][0], alpha * acc[i][j][1]);
         } else {
 #pragma unroll
-            for (int ib = 0; ib < 8; ib += 2) {
-                double2 old[2][4];
+            for (int ib = 0; ib < C::MT; ib += 2) {
+                double2 old[2][C::NT];
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < C::NT; ++j)
                         old[i][j] = *reinterpret_cast<const double2 *>(cbase + size_t((ib + i) * 8) * ldc + j * 8);
 #pragma unroll
                 for (int i = 0; i < 2; ++i)
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < C::NT; ++j)
                         *reinterpret_cast<double2 *>(cbase + size_t((ib + i) * 8) * ldc + j * 8) =
                             make_double2(alpha * acc[ib + i][j][0] + beta * old[i][j].x,
                                          alpha * acc[ib + i][j][1] + beta * old[i][j].y);
@@ -244,13 +250,13 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
         return;
     }
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-        const int row = m0 + wm * 64 + i * 8 + g;
+    for (int i = 0; i < C::MT; ++i) {
+        const int row = m0 + wm * C::MT * 8 + i * 8 + g;
         if (row >= M) continue;
         double *crow = Cmat + size_t(row) * ldc;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int col = n0 + wn * 32 + j * 8 + 2 * t;
+        for (int j = 0; j < C::NT; ++j) {
+            const int col = n0 + wn * C::NT * 8 + j * 8 + 2 * t;
             if (col >= N) continue;
             double v0 = alpha * acc[i][j][0];
             double v1 = alpha * acc[i][j][1];
@@ -303,7 +309,7 @@ int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size
 
 }  // namespace
 
-int g_dgemm_cfg = -1;  // -1 = auto, 0 = 128x64 (2 CTAs/SM), 1 = 128x128 (1 CTA/SM); rla_set_tuning("dgemm_cfg", v)
+int g_dgemm_cfg = -1;  // -1 = auto (6 for long-k products that fill the machine, else 0); rla_set_tuning("dgemm_cfg", 0..6)
 
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st) {
@@ -329,13 +335,15 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     // -1 (default): 128x128 tiles for long-k products that fill the machine several times over (2 % faster
     // there), the 2-CTA/SM 128x64 shape otherwise (rank-k updates, small and skinny products)
     int cfg = g_dgemm_cfg;
-    if (cfg < 0) cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? (aligned ? 2 : 1) : 0;
+    if (cfg < 0) cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? (aligned ? 6 : 1) : 0;
     if (cfg == 1) {
         return aligned ? launch_cfg<CfgLarge, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                        : launch_cfg<CfgLarge, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     }
     if (cfg == 2 && aligned) return launch_cfg<CfgLargeK32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     if (cfg == 3 && aligned) return launch_cfg<CfgSmallK32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    if (cfg == 5 && aligned) return launch_cfg<CfgW16, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    if (cfg == 6 && aligned) return launch_cfg<CfgW16K32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     return aligned ? launch_cfg<CfgSmall, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                    : launch_cfg<CfgSmall, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
