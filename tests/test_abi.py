@@ -56,7 +56,7 @@ def test_kernels_use_the_intended_pipes(rla):
     sg = [v for k, v in by_name.items() if "sgemm_ffma_kernel" in k]
     assert dg and sg
     for v in dg:
-        assert v.count("DMMA.8x8x4") >= 128 and "LDGSTS" in v
+        assert v.count("DMMA.8x8x4") >= 64 and "LDGSTS" in v
     for v in sg:
         assert v.count("FFMA2") >= 512 and "LDGSTS" in v
         assert "HMMA" not in v and "DMMA" not in v
