@@ -63,7 +63,7 @@ struct Context {
     cudaStream_t stream = nullptr;       // compute
     cudaStream_t copy_in = nullptr;      // H2D
     cudaStream_t copy_out = nullptr;     // D2H
-    Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync;
+    Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync, dTrsv;
     Buffer hSmall;                       // pinned scalars (info, perm)
     LuWorkspace lu_ws;
     std::vector<cudaEvent_t> events;
@@ -321,11 +321,11 @@ template <typename T>
 int getrs_core(size_t n, const T *dLU, size_t ld, const int64_t *dP, T *b) {
     Context &cx = tl_ctx;
     RLA_TRY(cx.dVec.ensure(n * sizeof(T)));
-    RLA_TRY(cx.dVec2.ensure(n * sizeof(T)));
+    RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(T)));
     RLA_TRY(cx.dInfo.ensure(64));
     RLA_TRY(cx.dSync.ensure(64));
     RLA_TRY(cx.hSmall.ensure(64));
-    T *dB = static_cast<T *>(cx.dVec.p), *dTmp = static_cast<T *>(cx.dVec2.p);
+    T *dB = static_cast<T *>(cx.dVec.p), *dTmp = static_cast<T *>(cx.dTrsv.p);
     int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p);
     int32_t *hInfo = static_cast<int32_t *>(cx.hSmall.p);
     RLA_CUDA(cudaMemcpyAsync(dB, b, n * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
@@ -389,7 +389,8 @@ int trsv_host(int lower, size_t n, const T *a, ptrdiff_t rs, T *x) {
     int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p), *hInfo = static_cast<int32_t *>(cx.hSmall.p);
     RLA_TRY(upload_matrix(dA, ld, a, size_t(rs), n, n, cx.stream));
     RLA_CUDA(cudaMemcpyAsync(dX, x, n * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
-    RLA_TRY(trsv_launch<T>(lower != 0, n, dA, ld, dX, dInfo, static_cast<int32_t *>(cx.dSync.p), cx.stream));
+    RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(T)));
+    RLA_TRY(trsv_launch<T>(lower != 0, n, dA, ld, dX, static_cast<T *>(cx.dTrsv.p), dInfo, static_cast<int32_t *>(cx.dSync.p), cx.stream));
     RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
     if (*hInfo != 0) return RLA_ERR_SINGULAR;
@@ -574,18 +575,18 @@ int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm,
                    void *stream) {
     RLA_TRY(ensure_ctx());
     Context &cx = tl_ctx;
-    RLA_TRY(cx.dVec2.ensure(n * sizeof(double)));
+    RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(double)));
     RLA_TRY(cx.dSync.ensure(64));
-    return getrs_launch<double>(n, lu, ld, d_perm, d_b, static_cast<double *>(cx.dVec2.p), d_info,
+    return getrs_launch<double>(n, lu, ld, d_perm, d_b, static_cast<double *>(cx.dTrsv.p), d_info,
                                 static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
 }
 int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, float *d_b, int32_t *d_info,
                    void *stream) {
     RLA_TRY(ensure_ctx());
     Context &cx = tl_ctx;
-    RLA_TRY(cx.dVec2.ensure(n * sizeof(float)));
+    RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(float)));
     RLA_TRY(cx.dSync.ensure(64));
-    return getrs_launch<float>(n, lu, ld, d_perm, d_b, static_cast<float *>(cx.dVec2.p), d_info,
+    return getrs_launch<float>(n, lu, ld, d_perm, d_b, static_cast<float *>(cx.dTrsv.p), d_info,
                                static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
 }
 size_t rla_lu_plan_bytes(void) { return lu_plan_bytes(); }

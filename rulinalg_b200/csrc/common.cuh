@@ -58,7 +58,7 @@ template <typename T>
 int getrf_launch(size_t n, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws,
                  cudaStream_t st);
 template <typename T>
-int getrs_launch(size_t n, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *d_tmp,
+int getrs_launch(size_t n, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *ws3,
                  int32_t *d_info, int32_t *d_flags, cudaStream_t st);
 
 template <typename T>
@@ -68,7 +68,7 @@ template <typename T>
 int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *x, size_t ldx, int32_t *d_info,
                        cudaStream_t st);
 template <typename T>
-int trsv_launch(bool lower, size_t n, const T *a, size_t ld, T *d_x, int32_t *d_info, int32_t *d_sync, cudaStream_t st);
+int trsv_launch(bool lower, size_t n, const T *a, size_t ld, T *d_x, T *ws2, int32_t *d_info, int32_t *d_sync, cudaStream_t st);
 template <typename T>
 int gemv_launch(size_t m, size_t n, const T *a, size_t lda, const T *x, T *y, cudaStream_t st);
 size_t lu_plan_bytes();

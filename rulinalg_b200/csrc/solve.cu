@@ -11,10 +11,11 @@
 //              with unfused multiply/add, so small systems are bit-identical to the reference.
 //   n  > 64  : trsv_kernel, HBM-bound blocked substitution.  Block rows of 64; a CTA per block row
 //              (ordered by an atomic ticket so dependencies always point at already-started CTAs)
-//              streams its row panel with 16-byte loads as soon as the x blocks it needs are
-//              published (monotonic `done` counter, release/acquire through __threadfence), keeps 8
-//              row accumulators per lane, then warp 0 solves the 64x64 diagonal block with shuffles.
-//              Summation order differs from the reference => tolerance-based parity.
+//              streams its row panel with 16-byte loads as soon as the x blocks it needs appear
+//              (the solution vector starts as a sentinel NaN pattern and is polled directly: no flag,
+//              fence or counter on the critical path), keeps 8 row accumulators per lane, and applies
+//              its pre-inverted 64x64 diagonal block as a mat-vec.  Summation order (and the explicit
+//              block inverse) differ from the reference => tolerance-based parity.
 #include <cfloat>
 
 #include "common.cuh"
@@ -101,13 +102,6 @@ getrs_small_kernel(int n, const T *__restrict__ lu, size_t ld, const int64_t *__
         }
 }
 
-// out[perm[i]] = in[i]
-template <typename T>
-__global__ void permute_vector_kernel(int n, const int64_t *__restrict__ perm, const T *__restrict__ in,
-                                      T *__restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[perm[i]] = in[i];
-}
 template <typename T>
 __global__ void copy_if_ok_kernel(int n, const T *__restrict__ in, T *__restrict__ out, const int32_t *__restrict__ info) {
     if (*info != 0) return;
@@ -122,37 +116,106 @@ template <typename T> struct Vec2;
 template <> struct Vec2<double> { using type = double2; };
 template <> struct Vec2<float> { using type = float2; };
 
-// sync words: [0] ticket, [1] done
-template <typename T, bool LOWER, bool UNIT = LOWER>
+// "not yet computed" marker for the solution vector: a quiet NaN with a payload no arithmetic produces
+template <typename T> struct Sentinel;
+template <> struct Sentinel<double> {
+    static __device__ __forceinline__ double v() { return __longlong_as_double(0x7FF8DEADBEEF0001ll); }
+    static __device__ __forceinline__ bool is(double x) { return __double_as_longlong(x) == 0x7FF8DEADBEEF0001ll; }
+};
+template <> struct Sentinel<float> {
+    static __device__ __forceinline__ float v() { return __uint_as_float(0x7FC0BEEFu); }
+    static __device__ __forceinline__ bool is(float x) { return __float_as_uint(x) == 0x7FC0BEEFu; }
+};
+__device__ __forceinline__ double ld_volatile(const double *p) { return *reinterpret_cast<const volatile double *>(p); }
+__device__ __forceinline__ float ld_volatile(const float *p) { return *reinterpret_cast<const volatile float *>(p); }
+
+// out[perm[i]] = in[i]  (perm == nullptr: plain copy); y1/y2 (optional) <- sentinel
+template <typename T>
+__global__ void trsv_prepare_kernel(int n, const int64_t *__restrict__ perm, const T *__restrict__ in, T *__restrict__ out,
+                                    T *__restrict__ y1, T *__restrict__ y2) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    out[perm ? perm[i] : i] = in[i];
+    if (y1) y1[i] = Sentinel<T>::v();
+    if (y2) y2[i] = Sentinel<T>::v();
+}
+
+// Blocked triangular solve  T x = rhs  (T = lower/upper triangle of `lu`, unit or explicit diagonal).
+// Block rows of 64; CTA per block row, taken in ticket order so every dependency belongs to a CTA that already
+// runs.  While the x blocks it depends on are still being produced a CTA (1) inverts its 64x64 diagonal block
+// (4 threads per column, registers + shuffles) and (2) streams its row panel with 16-byte loads, consuming each x
+// block as soon as it appears.  "Appears" = the values themselves: `xout` starts as a sentinel NaN pattern and
+// warp 0 polls the 64 values of the next block (no flag, no fence, no counter on the critical path); the step that
+// remains serial per block is poll -> 64x64 mat-vec with the pre-inverted diagonal block -> 64 stores.
+template <typename T, bool LOWER, bool UNIT>
 __global__ void __launch_bounds__(TRSV_THREADS, 2)
-trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int32_t *__restrict__ info) {
+trsv_kernel(int n, const T *__restrict__ lu, size_t ld, const T *__restrict__ rhs, T *xout, int32_t *ticket,
+            int32_t *__restrict__ info) {
     using V2 = typename Vec2<T>::type;
-    __shared__ T diag[TB * (TB + 1)];
+    __shared__ T dinv[TB * (TB + 1)];
+    __shared__ T xs[2][TB];
     __shared__ T rsum[TB];
+    __shared__ T vs[TB];
     __shared__ int sh_bid;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int nblk = (n + TB - 1) / TB;
-    if (tid == 0) sh_bid = atomicAdd(&sync[0], 1);
+    if (tid == 0) sh_bid = atomicAdd(ticket, 1);
     __syncthreads();
     const int ord = sh_bid;                       // 0,1,2,... in start order
     const int I = LOWER ? ord : nblk - 1 - ord;   // my block row
     const int row0 = I * TB;
-    volatile int32_t *done = sync + 1;
 
-    // prefetch the diagonal block (identity outside the matrix)
+    // diagonal block (identity outside the matrix) and this block's right-hand side
     for (int idx = tid; idx < TB * TB; idx += TRSV_THREADS) {
         const int r = idx / TB, c = idx - r * TB;
         T v = (r == c) ? T(1) : T(0);
-        if (row0 + r < n && row0 + c < n) v = lu[size_t(row0 + r) * ld + row0 + c];
-        diag[r * (TB + 1) + c] = v;
+        if (row0 + r < n && row0 + c < n && (LOWER ? c <= r : c >= r)) v = lu[size_t(row0 + r) * ld + row0 + c];
+        if (UNIT && r == c) v = T(1);
+        dinv[r * (TB + 1) + c] = v;
     }
+    T my_rhs = T(0);
+    if (tid < TB && row0 + tid < n) my_rhs = rhs[row0 + tid];
+    __syncthreads();
+
+    // ---- invert the diagonal block: thread (col j = tid>>2, residue r = tid&3) owns rows 4*ii + r of column j ----
+    {
+        const int j = tid >> 2, r = tid & 3;
+        if (!UNIT && r == 0 && row0 + j < n && fabs(dinv[j * (TB + 1) + j]) < EpsS<T>::v())
+            atomicMax(info, row0 + j + 1);        // back_/forward_substitution's |d_ii| < eps test (mod.rs:333-336, 374-377)
+        T x[TB / 4];
+#pragma unroll
+        for (int ii = 0; ii < TB / 4; ++ii) x[ii] = (4 * ii + r == j) ? T(1) : T(0);
+        const T *Dr = dinv + r * (TB + 1);
+        if (LOWER) {
+#pragma unroll
+            for (int k = 0; k < TB; ++k) {
+                if (r == (k & 3)) x[k >> 2] = UNIT ? x[k >> 2] : x[k >> 2] / dinv[k * (TB + 1) + k];
+                const T xk = __shfl_sync(0xffffffffu, x[k >> 2], (lane & ~3) | (k & 3));
+#pragma unroll
+                for (int ii = (k >> 2); ii < TB / 4; ++ii)
+                    if (ii > (k >> 2) || r > (k & 3)) x[ii] -= Dr[(4 * ii) * (TB + 1) + k] * xk;
+            }
+        } else {
+#pragma unroll
+            for (int k = TB - 1; k >= 0; --k) {
+                if (r == (k & 3)) x[k >> 2] = x[k >> 2] / dinv[k * (TB + 1) + k];
+                const T xk = __shfl_sync(0xffffffffu, x[k >> 2], (lane & ~3) | (k & 3));
+#pragma unroll
+                for (int ii = 0; ii <= (k >> 2); ++ii)
+                    if (ii < (k >> 2) || r < (k & 3)) x[ii] -= Dr[(4 * ii) * (TB + 1) + k] * xk;
+            }
+        }
+        __syncthreads();                          // everybody finished reading D
+#pragma unroll
+        for (int ii = 0; ii < TB / 4; ++ii) dinv[(4 * ii + r) * (TB + 1) + j] = x[ii];
+    }
+    // (visibility of dinv is guaranteed by the __syncthreads inside / after the streaming loop below)
 
     const bool vec_ok = ((ld & 1) == 0) && ((reinterpret_cast<uintptr_t>(lu) & (2 * sizeof(T) - 1)) == 0);
     T acc[8];
 #pragma unroll
     for (int q = 0; q < 8; ++q) acc[q] = T(0);
     const int nd = LOWER ? I : nblk - 1 - I;      // number of dependency blocks
-    int seen = 0;                                 // cached `done`
     V2 lcur[8];
     auto load_tiles = [&](int Jb, V2 *dst) {
         const int col = Jb * TB + 2 * lane;
@@ -177,20 +240,21 @@ trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int
     if (nd > 0) load_tiles(LOWER ? 0 : nblk - 1, lcur);
     for (int t = 0; t < nd; ++t) {
         const int Jb = LOWER ? t : nblk - 1 - t;
-        if (seen < t + 1) {
-            // whole warp polls (a spin loop in a partially active warp is several times slower)
-            int s;
-            while ((s = *done) < t + 1) {
-            }
-            seen = __shfl_sync(0xffffffffu, s, 0);
-            __threadfence();
+        if (warp == 0) {
+            // the whole warp polls the 64 values of block Jb (2 per lane); indices past n are clamped
+            const int c0 = min(Jb * TB + 2 * lane, n - 1), c1 = min(Jb * TB + 2 * lane + 1, n - 1);
+            T a, b;
+            do {
+                a = ld_volatile(xout + c0);
+                b = ld_volatile(xout + c1);
+            } while (Sentinel<T>::is(a) || Sentinel<T>::is(b));
+            xs[t & 1][2 * lane] = (Jb * TB + 2 * lane < n) ? a : T(0);
+            xs[t & 1][2 * lane + 1] = (Jb * TB + 2 * lane + 1 < n) ? b : T(0);
         }
-        const int col = Jb * TB + 2 * lane;
-        T x0 = T(0), x1 = T(0);
-        if (col < n) x0 = __ldcg(x + col);
-        if (col + 1 < n) x1 = __ldcg(x + col + 1);
         V2 lnext[8];
         if (t + 1 < nd) load_tiles(LOWER ? t + 1 : nblk - 2 - t, lnext);
+        __syncthreads();
+        const T x0 = xs[t & 1][2 * lane], x1 = xs[t & 1][2 * lane + 1];
 #pragma unroll
         for (int q = 0; q < 8; ++q) acc[q] += lcur[q].x * x0 + lcur[q].y * x1;
         if (t + 1 < nd) {
@@ -206,59 +270,27 @@ trsv_kernel(int n, const T *__restrict__ lu, size_t ld, T *x, int32_t *sync, int
         if (lane == 0) rsum[warp * 8 + q] = v;
     }
     __syncthreads();
-    if (warp == 0) {
-        // rows lane and lane+32 of the block
-        const int ra = lane, rb = lane + 32;
-        T va = (row0 + ra < n) ? sub_rn(__ldcg(x + row0 + ra), rsum[ra]) : T(0);
-        T vb = (row0 + rb < n) ? sub_rn(__ldcg(x + row0 + rb), rsum[rb]) : T(0);
-        if (LOWER) {
-            T ia = T(1), ib = T(1);
-            if (!UNIT) {
-                // forward_substitution (src/matrix/mod.rs:363-398): |l_ii| < eps -> DivByZero, then divide
-                const T da = diag[ra * (TB + 1) + ra], db = diag[rb * (TB + 1) + rb];
-                if (row0 + ra < n && fabs(da) < EpsS<T>::v()) atomicCAS(info, 0, row0 + ra + 1);
-                if (row0 + rb < n && fabs(db) < EpsS<T>::v()) atomicCAS(info, 0, row0 + rb + 1);
-                ia = div_rn(T(1), da);
-                ib = div_rn(T(1), db);
-            }
-#pragma unroll 8
-            for (int k = 0; k < TB; ++k) {
-                if (!UNIT && lane == (k & 31)) {
-                    if (k < 32) va *= ia; else vb *= ib;
-                }
-                const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
-                if (ra > k) va -= diag[ra * (TB + 1) + k] * xk;
-                if (rb > k) vb -= diag[rb * (TB + 1) + k] * xk;
-            }
-        } else {
-            // |u_ii| < eps check (mod.rs:333-336) and reciprocals for both owned rows up front, so the
-            // 64-step dependent chain below carries a multiply instead of an IEEE division
-            const T da = diag[ra * (TB + 1) + ra], db = diag[rb * (TB + 1) + rb];
-            if (row0 + ra < n && fabs(da) < EpsS<T>::v()) atomicCAS(info, 0, row0 + ra + 1);
-            if (row0 + rb < n && fabs(db) < EpsS<T>::v()) atomicCAS(info, 0, row0 + rb + 1);
-            const T ia = div_rn(T(1), da), ib = div_rn(T(1), db);
-#pragma unroll 8
-            for (int k = TB - 1; k >= 0; --k) {
-                if (lane == (k & 31)) {
-                    if (k < 32) va *= ia; else vb *= ib;
-                }
-                const T xk = __shfl_sync(0xffffffffu, (k < 32) ? va : vb, k & 31);
-                if (ra < k) va -= diag[ra * (TB + 1) + k] * xk;
-                if (rb < k) vb -= diag[rb * (TB + 1) + k] * xk;
-            }
+    if (tid < TB) vs[tid] = sub_rn(my_rhs, rsum[tid]);
+    __syncthreads();
+    {
+        // x_I = D^-1 v : 4 threads per row, 16 columns each
+        const int r = tid >> 2, part = tid & 3;
+        T sum = T(0);
+#pragma unroll
+        for (int c = 0; c < TB / 4; ++c) sum += dinv[r * (TB + 1) + part * (TB / 4) + c] * vs[part * (TB / 4) + c];
+        sum += __shfl_xor_sync(0xffffffffu, sum, 1);
+        sum += __shfl_xor_sync(0xffffffffu, sum, 2);
+        if (part == 0 && row0 + r < n) {
+            if (Sentinel<T>::is(sum)) sum = T(nan(""));           // never publish the marker itself (canonical NaN instead)
+            *reinterpret_cast<volatile T *>(xout + row0 + r) = sum;
         }
-        if (row0 + ra < n) x[row0 + ra] = va;
-        if (row0 + rb < n) x[row0 + rb] = vb;
-        __threadfence();
-        __syncwarp();
-        if (lane == 0) atomicAdd(&sync[1], 1);    // blocks complete in dependency order => counter == #done
     }
 }
 
 }  // namespace
 
 template <typename T>
-int getrs_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *d_tmp, int32_t *d_info,
+int getrs_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *ws3, int32_t *d_info,
                  int32_t *d_sync, cudaStream_t st) {
     if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
     const int n = int(n_);
@@ -270,17 +302,45 @@ int getrs_launch(size_t n_, const T *lu, size_t ld, const int64_t *d_perm, T *d_
         return RLA_OK;
     }
     const int nblk = (n + TB - 1) / TB;
-    permute_vector_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, d_perm, d_b, d_tmp);
+    T *pb = ws3, *y = ws3 + n, *x = ws3 + 2 * size_t(n);     // P b | L^-1 P b | U^-1 L^-1 P b
+    trsv_prepare_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, d_perm, d_b, pb, y, x);
     RLA_LAUNCHED();
     RLA_CUDA(cudaMemsetAsync(d_sync, 0, 4 * sizeof(int32_t), st));
-    trsv_kernel<T, true><<<nblk, TRSV_THREADS, 0, st>>>(n, lu, ld, d_tmp, d_sync, d_info);
+    trsv_kernel<T, true, true><<<nblk, TRSV_THREADS, 0, st>>>(n, lu, ld, pb, y, d_sync, d_info);
     RLA_LAUNCHED();
-    trsv_kernel<T, false><<<nblk, TRSV_THREADS, 0, st>>>(n, lu, ld, d_tmp, d_sync + 2, d_info);
+    trsv_kernel<T, false, false><<<nblk, TRSV_THREADS, 0, st>>>(n, lu, ld, y, x, d_sync + 1, d_info);
     RLA_LAUNCHED();
-    copy_if_ok_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, d_tmp, d_b, d_info);
+    copy_if_ok_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, x, d_b, d_info);
     RLA_LAUNCHED();
     return RLA_OK;
 }
+
+// solve_l_triangular / solve_u_triangular (src/matrix/base/mod.rs:1015-1067 -> forward_/back_substitution,
+// src/matrix/mod.rs:318-398): triangular part of a general matrix, diagonal included, |diag| < eps -> DivByZero.
+// d_x holds y on entry, x on exit (untouched when *d_info != 0).  ws2: 2n elements of workspace.
+template <typename T>
+int trsv_launch(bool lower, size_t n_, const T *a, size_t ld, T *d_x, T *ws2, int32_t *d_info, int32_t *d_sync,
+                cudaStream_t st) {
+    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
+    if (n == 0) return RLA_OK;
+    const int nblk = (n + TB - 1) / TB;
+    T *rhs = ws2, *x = ws2 + n;
+    trsv_prepare_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, nullptr, d_x, rhs, x, nullptr);
+    RLA_LAUNCHED();
+    RLA_CUDA(cudaMemsetAsync(d_sync, 0, 4 * sizeof(int32_t), st));
+    if (lower)
+        trsv_kernel<T, true, false><<<nblk, TRSV_THREADS, 0, st>>>(n, a, ld, rhs, x, d_sync, d_info);
+    else
+        trsv_kernel<T, false, false><<<nblk, TRSV_THREADS, 0, st>>>(n, a, ld, rhs, x, d_sync, d_info);
+    RLA_LAUNCHED();
+    copy_if_ok_kernel<T><<<(n + 255) / 256, 256, 0, st>>>(n, x, d_x, d_info);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+template int trsv_launch<double>(bool, size_t, const double *, size_t, double *, double *, int32_t *, int32_t *, cudaStream_t);
+template int trsv_launch<float>(bool, size_t, const float *, size_t, float *, float *, int32_t *, int32_t *, cudaStream_t);
 
 // inverse of a factorisation with n <= 64: n exact-order solves, one warp each (bit-identical to the reference)
 template <typename T>
@@ -293,27 +353,6 @@ int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *
 }
 template int getri_small_launch<double>(int, const double *, size_t, const int64_t *, double *, size_t, int32_t *, cudaStream_t);
 template int getri_small_launch<float>(int, const float *, size_t, const int64_t *, float *, size_t, int32_t *, cudaStream_t);
-
-// solve_l_triangular / solve_u_triangular (src/matrix/base/mod.rs:1015-1067 -> forward_/back_substitution,
-// src/matrix/mod.rs:318-398): triangular part of a general matrix, diagonal included, |diag| < eps -> DivByZero.
-// d_x holds y on entry, x on exit (unspecified when *d_info != 0).
-template <typename T>
-int trsv_launch(bool lower, size_t n_, const T *a, size_t ld, T *d_x, int32_t *d_info, int32_t *d_sync, cudaStream_t st) {
-    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
-    const int n = int(n_);
-    RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
-    if (n == 0) return RLA_OK;
-    const int nblk = (n + TB - 1) / TB;
-    RLA_CUDA(cudaMemsetAsync(d_sync, 0, 4 * sizeof(int32_t), st));
-    if (lower)
-        trsv_kernel<T, true, false><<<nblk, TRSV_THREADS, 0, st>>>(n, a, ld, d_x, d_sync, d_info);
-    else
-        trsv_kernel<T, false, false><<<nblk, TRSV_THREADS, 0, st>>>(n, a, ld, d_x, d_sync, d_info);
-    RLA_LAUNCHED();
-    return RLA_OK;
-}
-template int trsv_launch<double>(bool, size_t, const double *, size_t, double *, int32_t *, int32_t *, cudaStream_t);
-template int trsv_launch<float>(bool, size_t, const float *, size_t, float *, int32_t *, int32_t *, cudaStream_t);
 
 template int getrs_launch<double>(size_t, const double *, size_t, const int64_t *, double *, double *, int32_t *,
                                   int32_t *, cudaStream_t);
