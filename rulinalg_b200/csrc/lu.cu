@@ -130,6 +130,7 @@ __device__ __forceinline__ unsigned long long gtime() {
 constexpr int HUB_ROOT_WARPS = 5;                 // 160 threads >= G
 constexpr int HUB_ROOT_THREADS = HUB_ROOT_WARPS * 32;
 constexpr int HUB_SWAP_T0 = 192;                  // warps 6..15 apply the interchanges
+constexpr int DIRECT_G = 160;                     // up to this many row CTAs every CTA reads the packets itself (measured: best at every G <= 147)
 
 template <typename T>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
@@ -148,6 +149,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    const int direct_g = (dbg >> 8) ? (dbg >> 8) : DIRECT_G;
 
     if (b >= G) {
         // =========================== hub CTA ===========================
@@ -347,18 +349,42 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             if (owns_d && tid >= 64 && tid < 64 + jb)
                 msg_store(sc.diagbuf + par * PW + (tid - 64), bits_of(s[(d - r0) * PLDS + (tid - 64)]), tag_hi);
         }
-        // ---- wait for the hub's verdict ----
+        // ---- the verdict: small grids (G <= DIRECT_G) read the candidate packets themselves -- one hop instead of two,
+        //      and 32 CTAs polling 32 packets is no hot spot; larger grids wait for the hub's single result message ----
         if (warp == 0) {
-            // the WHOLE warp polls the same address: a spin loop in a partially active warp is several
-            // times slower on this part (measured: 5.4 vs 3.1 us per column)
-            unsigned long long rlo, rhi;
-            do {
-                msg_load(sc.result + par, rlo, rhi);
-            } while (unsigned(rhi >> 32) != tag);
-            if (lane == 0) {
-                sh_idx = int(unsigned(rlo & 0xffffffffull));
-                sh_win = int(unsigned(rlo >> 32));
-                sh_sing = int(rhi & 1ull);
+            if (G <= direct_g) {
+                // whole warp polls, ceil(G/32) packets per lane; lanes past G duplicate packet G-1
+                unsigned long long gk = 0ull;
+                int gi = INT_MAX, gw = 0;
+                for (int base = 0; base < G; base += 32) {
+                    const int q = min(base + lane, G - 1);
+                    unsigned long long lo, hi;
+                    do {
+                        msg_load(sc.packets + par * GMAX + q, lo, hi);
+                    } while (unsigned(hi >> 32) != tag);
+                    const int i1 = int(unsigned(hi & 0xffffffffull));
+                    if (lo > gk || (lo == gk && i1 < gi)) { gk = lo; gi = i1; gw = q; }
+                }
+                unsigned wm;
+                warp_argmax(gk, gi, wm);
+                gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
+                if (lane == 0) {
+                    sh_idx = gi;
+                    sh_win = gw;
+                    sh_sing = (T(__longlong_as_double((long long)gk)) < Eps<T>::v()) ? 1 : 0;   // same test as the hub
+                }
+            } else {
+                // the WHOLE warp polls the same address: a spin loop in a partially active warp is several
+                // times slower on this part (measured: 5.4 vs 3.1 us per column)
+                unsigned long long rlo, rhi;
+                do {
+                    msg_load(sc.result + par, rlo, rhi);
+                } while (unsigned(rhi >> 32) != tag);
+                if (lane == 0) {
+                    sh_idx = int(unsigned(rlo & 0xffffffffull));
+                    sh_win = int(unsigned(rlo >> 32));
+                    sh_sing = int(rhi & 1ull);
+                }
             }
         }
         __syncthreads();

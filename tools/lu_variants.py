@@ -15,12 +15,8 @@ def run(n, reps=3):
         e0.record(); rla.check(l.rla_dgetrf_dev(n, a.data_ptr(), n, perm.data_ptr(), info.data_ptr(), s)); e1.record(); e1.synchronize()
         best = min(best, e0.elapsed_time(e1))
     return best
-for n in (16384, 32768):
-    for dbg in (0,):
-        for gmax in (147, 128, 112, 96, 84, 64):
-            l.rla_set_tuning(b"lu_gmax", gmax); l.rla_set_tuning(b"lu_dbg", dbg)
-            try:
-                ms = run(n)
-            except Exception as e:
-                ms = None
-            print(json.dumps(dict(n=n, dbg=dbg, gmax=gmax, ms=ms)), flush=True)
+for n in (8192, 16384, 32768):
+    for thr in (64, 96, 128, 147):
+        l.rla_set_tuning(b"lu_gmax", 147 if thr > 112 else 112); l.rla_set_tuning(b"lu_dbg", thr << 8)
+        ms = run(n)
+        print(json.dumps(dict(n=n, direct_g=thr, ms=ms)), flush=True)
