@@ -70,16 +70,16 @@ __device__ __forceinline__ void warp_argmax(unsigned long long &key, int &idx, u
 // One grid-wide exchange per column, through 16-byte self-validating messages {payload, tag}
 // (tags are unique per (panel launch, column); a 16-byte aligned store is single-copy atomic, so no
 // fence is needed between a message and the data it announces -- every piece carries its own tag):
-//   row CTA  -> candidate packet {|max|, row index, tag} + the candidate row as 64 tagged chunks
-//   hub CTA  -> polls the G packets with G threads (the only heavy poller in the grid), reduces, and
-//               publishes ONE result message {pivot row, winning CTA, singular flag, tag}
-//   row CTAs -> one thread polls the result, then 64 threads fetch the winner's tagged row chunks.
+//   every row CTA publishes a candidate packet {|max| key, row index, tag} + the candidate row as 64
+//   tagged chunks, then reads ALL G packets with one whole warp (ceil(G/32) per lane), reduces them
+//   (every CTA reaches the same verdict), and fetches the winner's tagged row chunks.
 // Buffers alternate by column parity; a row CTA can be at most one column ahead of the slowest one
-// because the hub needs every packet to publish the next result.
+// because it needs everybody's packet to advance.
 //
-// The hub's remaining warps use the pivots as they are decided: one warp folds each interchange into
-// the outer block's net-permutation plan (consumed by laswp_apply_kernel), ten warps apply it to the
-// columns of the outer block that lie outside this panel.  Nobody ever waits for them.
+// Row CTA 0 also appends each verdict to a tagged pivot log (one slot per column, never reused within a
+// launch).  The hub CTA follows that log at its own pace -- nobody ever waits for it: one warp folds each
+// interchange into the outer block's net-permutation plan (consumed by laswp_apply_kernel), ten warps apply
+// it to the columns of the outer block that lie outside this panel.
 // -------------------------------------------------------------------------------------------
 struct __align__(16) Msg {
     unsigned long long lo, hi;
@@ -115,7 +115,7 @@ struct PanelScratch {
     Msg *packets;                    // [2][GMAX]       {bits(|max| as f64), idx | tag<<32}
     Msg *rowbuf;                     // [2][GMAX][PW]   {bits(value), tag}
     Msg *diagbuf;                    // [2][PW]         {bits(value), tag}
-    Msg *result;                     // [2]             {pivot idx | win<<32, singular | tag<<32}
+    unsigned long long *piv_log;     // [PW]            tag<<32 | pivot row (0xffffffff = singular), written by row CTA 0
     PlanState *state;
     LaswpPlan *plan;
     int32_t *rowid;
@@ -127,10 +127,8 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 #define TRACE(slot) do { if (sc.trace && tid == 0) sc.trace[c * 8 + (slot)] = gtime(); } while (0)
-constexpr int HUB_ROOT_WARPS = 5;                 // 160 threads >= G
-constexpr int HUB_ROOT_THREADS = HUB_ROOT_WARPS * 32;
+constexpr int HUB_PLAN_WARP = 5;                  // hub warp 0 follows the pivot log, warp 5 maintains the plan
 constexpr int HUB_SWAP_T0 = 192;                  // warps 6..15 apply the interchanges
-constexpr int DIRECT_G = 160;                     // up to this many row CTAs every CTA reads the packets itself (measured: best at every G <= 147)
 
 template <typename T>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
@@ -142,14 +140,12 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
     __shared__ T prow_s[PW];
     __shared__ unsigned long long red_key[2][PANEL_THREADS / 32];
     __shared__ int red_idx[2][PANEL_THREADS / 32];
-    __shared__ int red_win[2][PANEL_THREADS / 32];
     __shared__ T sh_abs;
     __shared__ int sh_idx, sh_win, sh_sing;
     __shared__ int piv_sm[PW];
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int direct_g = (dbg >> 8) ? (dbg >> 8) : DIRECT_G;
 
     if (b >= G) {
         // =========================== hub CTA ===========================
@@ -169,59 +165,18 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         for (int i = tid; i < PW; i += PANEL_THREADS) piv_sm[i] = INT_MIN;
         __syncthreads();
 
-        if (warp < HUB_ROOT_WARPS) {
-            // ---- root: gather G candidate packets, reduce, publish the result ----
+        if (warp == 0) {
+            // ---- follower: the pivot log written by row CTA 0 (one tagged 8-byte entry per column, never
+            //      overwritten within a launch, so the hub may lag by any number of columns) -> shared memory ----
             for (int c = 0; c < jb; ++c) {
-                const int par = c & 1;
-                const unsigned tag = tag_base + unsigned(c) + 1u;
-                unsigned long long gk = 0ull;
-                int gi = INT_MAX, gw = 0;
-                // whole warps poll: lanes past G re-read packet G-1 (a duplicate candidate is harmless),
-                // so no polling warp is ever partially active
-                if ((tid & ~31) < G) {
-                    const int q = min(tid, G - 1);
-                    unsigned long long lo, hi;
-                    do {
-                        msg_load(sc.packets + par * GMAX + q, lo, hi);
-                    } while (unsigned(hi >> 32) != tag);
-                    gk = lo;                                  // already a key (non-negative f64 bits)
-                    gi = int(unsigned(hi & 0xffffffffull));
-                    gw = q;
-                }
-                {
-                    unsigned wm;
-                    warp_argmax(gk, gi, wm);
-                    gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
-                }
-                if (lane == 0) { red_key[par][warp] = gk; red_idx[par][warp] = gi; red_win[par][warp] = gw; }
-                asm volatile("bar.sync 1, %0;" ::"n"(HUB_ROOT_THREADS) : "memory");
-                TRACE(5);
-                int sing = 0;
-                if (warp == 0) {
-                    gk = (lane < HUB_ROOT_WARPS) ? red_key[par][lane] : 0ull;
-                    gi = (lane < HUB_ROOT_WARPS) ? red_idx[par][lane] : INT_MAX;
-                    gw = (lane < HUB_ROOT_WARPS) ? red_win[par][lane] : 0;
-                    unsigned wm;
-                    warp_argmax(gk, gi, wm);
-                    gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
-                    if (lane == 0) {
-                        const T gv = T(__longlong_as_double((long long)gk));
-                        sing = (gv < Eps<T>::v()) ? 1 : 0;         // lu.rs:179-183 (NaN: false, continues)
-                        msg_store(sc.result + par, (unsigned long long)(unsigned)gi | ((unsigned long long)(unsigned)gw << 32),
-                                  (unsigned long long)sing | ((unsigned long long)tag << 32));
-                        if (sing) {
-                            *info = J + c + 1;
-                        } else {
-                            ipiv[J + c] = gi;
-                        }
-                        *((volatile int *)&piv_sm[c]) = sing ? -1 : gi;
-                        if (sc.trace) sc.trace[c * 8 + 6] = gtime();
-                    }
-                    sing = __shfl_sync(0xffffffffu, sing, 0);
-                    if (lane == 0) sh_sing = sing;
-                }
-                asm volatile("bar.sync 1, %0;" ::"n"(HUB_ROOT_THREADS) : "memory");
-                if (*((volatile int *)&sh_sing) && *((volatile int *)&piv_sm[c]) == -1) return;
+                const unsigned want = tag_base + unsigned(c) + 1u;
+                unsigned long long v;
+                do {
+                    v = *((volatile unsigned long long *)(sc.piv_log + c));
+                } while (unsigned(v >> 32) != want);
+                const int p = int(unsigned(v & 0xffffffffull));      // -1 = singular
+                if (lane == 0) *((volatile int *)&piv_sm[c]) = p;
+                if (p < 0) return;
             }
             return;
         }
@@ -232,14 +187,14 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int t2 = tid - HUB_SWAP_T0;
         const int col = (t2 < na) ? sw_c0a + t2 : sw_c0b + (t2 - na);
         int nf = st.nf;
-        if (warp != HUB_ROOT_WARPS && (t2 < 0 || t2 >= ncols)) return;
+        if (warp != HUB_PLAN_WARP && (t2 < 0 || t2 >= ncols)) return;
         for (int c = 0; c < jb; ++c) {
             int p;
             while ((p = *((volatile int *)&piv_sm[c])) == INT_MIN) __nanosleep(200);   // never compete with the root warps
             if (p < 0) return;                       // singular
             const int d = J + c;
             if (p == d) continue;
-            if (warp == HUB_ROOT_WARPS) {
+            if (warp == HUB_PLAN_WARP) {
                 // plan warp
                 const int k = d - J0;                // dense index of the diagonal row
                 if (p < J0 + w) {
@@ -266,7 +221,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                 *rp = vd;
             }
         }
-        if (warp == HUB_ROOT_WARPS) {
+        if (warp == HUB_PLAN_WARP) {
             if (!last) {
                 for (int i = lane; i < LASWP_MAXJB; i += 32) {
                     sc.state->od[i] = st.od[i];
@@ -349,48 +304,39 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             if (owns_d && tid >= 64 && tid < 64 + jb)
                 msg_store(sc.diagbuf + par * PW + (tid - 64), bits_of(s[(d - r0) * PLDS + (tid - 64)]), tag_hi);
         }
-        // ---- the verdict: small grids (G <= DIRECT_G) read the candidate packets themselves -- one hop instead of two,
-        //      and 32 CTAs polling 32 packets is no hot spot; larger grids wait for the hub's single result message ----
+        // ---- the verdict: every row CTA reads the G candidate packets itself with ONE whole warp (ceil(G/32)
+        //      packets per lane; lanes past G duplicate packet G-1 so the warp is never partially active) ----
         if (warp == 0) {
-            if (G <= direct_g) {
-                // whole warp polls, ceil(G/32) packets per lane; lanes past G duplicate packet G-1
-                unsigned long long gk = 0ull;
-                int gi = INT_MAX, gw = 0;
-                for (int base = 0; base < G; base += 32) {
-                    const int q = min(base + lane, G - 1);
-                    unsigned long long lo, hi;
-                    do {
-                        msg_load(sc.packets + par * GMAX + q, lo, hi);
-                    } while (unsigned(hi >> 32) != tag);
-                    const int i1 = int(unsigned(hi & 0xffffffffull));
-                    if (lo > gk || (lo == gk && i1 < gi)) { gk = lo; gi = i1; gw = q; }
-                }
-                unsigned wm;
-                warp_argmax(gk, gi, wm);
-                gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
-                if (lane == 0) {
-                    sh_idx = gi;
-                    sh_win = gw;
-                    sh_sing = (T(__longlong_as_double((long long)gk)) < Eps<T>::v()) ? 1 : 0;   // same test as the hub
-                }
-            } else {
-                // the WHOLE warp polls the same address: a spin loop in a partially active warp is several
-                // times slower on this part (measured: 5.4 vs 3.1 us per column)
-                unsigned long long rlo, rhi;
+            unsigned long long gk = 0ull;
+            int gi = INT_MAX, gw = 0;
+            for (int base = 0; base < G; base += 32) {
+                const int q = min(base + lane, G - 1);
+                unsigned long long lo, hi;
                 do {
-                    msg_load(sc.result + par, rlo, rhi);
-                } while (unsigned(rhi >> 32) != tag);
-                if (lane == 0) {
-                    sh_idx = int(unsigned(rlo & 0xffffffffull));
-                    sh_win = int(unsigned(rlo >> 32));
-                    sh_sing = int(rhi & 1ull);
+                    msg_load(sc.packets + par * GMAX + q, lo, hi);
+                } while (unsigned(hi >> 32) != tag);
+                const int i1 = int(unsigned(hi & 0xffffffffull));
+                if (lo > gk || (lo == gk && i1 < gi)) { gk = lo; gi = i1; gw = q; }
+            }
+            unsigned wm;
+            warp_argmax(gk, gi, wm);
+            gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
+            if (lane == 0) {
+                const int sing = (T(__longlong_as_double((long long)gk)) < Eps<T>::v()) ? 1 : 0;   // lu.rs:179-183
+                sh_idx = gi;
+                sh_win = gw;
+                sh_sing = sing;
+                if (b == 0) {                      // CTA 0 keeps the books: pivot log for the hub, ipiv, info
+                    *((volatile unsigned long long *)(sc.piv_log + c)) =
+                        tag_hi | (sing ? 0xffffffffull : (unsigned long long)(unsigned)gi);
+                    if (sing) *info = d + 1; else ipiv[d] = gi;
                 }
             }
         }
         __syncthreads();
         if (b == 0) TRACE(2);
         const int prow_idx = sh_idx, win = sh_win;
-        if (sh_sing) return;                       // uniform across the grid; the hub set *info
+        if (sh_sing) return;                       // uniform across the grid (every CTA reduces the same packets)
         if ((tid & ~31) < jb) {                   // whole warps poll (lanes past jb re-read chunk jb-1)
             unsigned long long vlo, vhi;
             const Msg *src = sc.rowbuf + size_t(par * GMAX + win) * PW + min(tid, jb - 1);
@@ -662,7 +608,7 @@ constexpr size_t SC_PACKETS = 0;
 constexpr size_t SC_ROWBUF = SC_PACKETS + 2 * GMAX * sizeof(Msg);
 constexpr size_t SC_DIAGBUF = SC_ROWBUF + size_t(2) * GMAX * PW * sizeof(Msg);
 constexpr size_t SC_RESULT = SC_DIAGBUF + 2 * PW * sizeof(Msg);
-constexpr size_t SC_PLAN = SC_RESULT + 256;
+constexpr size_t SC_PLAN = SC_RESULT + ((PW * 8 + 255) / 256) * 256;
 constexpr size_t SC_STATE = SC_PLAN + ((sizeof(LaswpPlan) + 255) / 256) * 256;
 constexpr size_t SC_TOTAL = SC_STATE + sizeof(PlanState) + 256;
 
@@ -702,7 +648,7 @@ PanelScratch scratch_view(LuWorkspace &ws) {
     sc.packets = reinterpret_cast<Msg *>(sp + SC_PACKETS);
     sc.rowbuf = reinterpret_cast<Msg *>(sp + SC_ROWBUF);
     sc.diagbuf = reinterpret_cast<Msg *>(sp + SC_DIAGBUF);
-    sc.result = reinterpret_cast<Msg *>(sp + SC_RESULT);
+    sc.piv_log = reinterpret_cast<unsigned long long *>(sp + SC_RESULT);
     sc.plan = reinterpret_cast<LaswpPlan *>(sp + SC_PLAN);
     sc.state = reinterpret_cast<PlanState *>(sp + SC_STATE);
     sc.rowid = nullptr;
@@ -732,7 +678,7 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
     for (int j = J0; j < J0 + w; j += PW) {
         const int jb = min(PW, J0 + w - j);
         const int nrem = n - j;
-        int G = min(min(min(g_num_sms - 1, HUB_ROOT_THREADS), g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
+        int G = min(min(g_num_sms - 1, g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
         while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
         int R = (nrem + G - 1) / G;
         size_t smem = size_t(R) * PLDS * sizeof(T);

@@ -17,8 +17,8 @@ torch.cuda.synchronize()
 buf = (ctypes.c_ulonglong * 512)()
 rla.check(l.rla_debug_lu_trace(buf))
 t = np.array(buf, dtype=np.int64).reshape(64, 8)
-names = ["start->packet (local argmax)", "packet->hub has all", "hub reduce->result stored", "result stored->CTA0 sees", "CTA0 row fetch+swap", "div+update", "column total"]
-d = np.stack([t[:, 1] - t[:, 0], t[:, 5] - t[:, 1], t[:, 6] - t[:, 5], t[:, 2] - t[:, 6], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 4] - t[:, 0]], axis=1)
+names = ["start->packet (local argmax)", "unused", "unused", "packet->verdict", "row fetch+swap", "div+update", "column total"]
+d = np.stack([t[:, 1] - t[:, 0], 0 * t[:, 0], 0 * t[:, 0], t[:, 2] - t[:, 1], t[:, 3] - t[:, 2], t[:, 4] - t[:, 3], t[:, 4] - t[:, 0]], axis=1)
 print("n =", n, " info", int(info.item()))
 for i, nm in enumerate(names):
     print(f"{nm:34s} median {np.median(d[4:, i]):8.0f} ns   mean {d[4:, i].mean():8.0f}   min {d[4:, i].min():6d} max {d[4:, i].max():6d}")
