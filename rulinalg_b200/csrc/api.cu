@@ -634,7 +634,7 @@ int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, ui
 int rla_set_tuning(const char *key, int value) {
     if (!key) return RLA_ERR_INVALID;
     if (strcmp(key, "dgemm_cfg") == 0) {
-        if (value < -1 || value > 6) return RLA_ERR_INVALID;
+        if (value < -1 || value > 7) return RLA_ERR_INVALID;
         g_dgemm_cfg = value;
         return RLA_OK;
     }

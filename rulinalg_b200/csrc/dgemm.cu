@@ -54,6 +54,7 @@ using CfgLargeK32 = Cfg<128, 128, 2, 4, 3, 1, 32>;
 using CfgSmallK32 = Cfg<128, 64, 2, 2, 2, 2, 32>;
 using CfgW16 = Cfg<128, 128, 4, 4, 4, 1, 16>;       // 16 warps, 32x32 warp tiles: 4 warps per scheduler
 using CfgW16K32 = Cfg<128, 128, 4, 4, 3, 1, 32>;
+using CfgTiny = Cfg<64, 64, 2, 2, 3, 4, 16>;         // 64x64 tiles for products too small to fill the SMs with 128x64
 
 // Per-thread copy plan for the aligned (16-byte) path.  Thread `tid` always copies chunk column
 // `tid % chunks_per_row` of rows `tid / chunks_per_row + i * rows_per_pass`: one base pointer per
@@ -344,6 +345,7 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     if (cfg == 3 && aligned) return launch_cfg<CfgSmallK32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     if (cfg == 5 && aligned) return launch_cfg<CfgW16, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     if (cfg == 6 && aligned) return launch_cfg<CfgW16K32, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    if (cfg == 7 && aligned) return launch_cfg<CfgTiny, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
     return aligned ? launch_cfg<CfgSmall, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                    : launch_cfg<CfgSmall, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
