@@ -310,7 +310,7 @@ int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size
 
 }  // namespace
 
-int g_dgemm_cfg = -1;  // -1 = auto (6 for long-k products that fill the machine, else 0); rla_set_tuning("dgemm_cfg", 0..6)
+int g_dgemm_cfg = -1;  // -1 = auto (cost model below); rla_set_tuning("dgemm_cfg", 0..7) forces one
 
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st) {
@@ -333,10 +333,22 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     const bool aligned = ((lda & 1) == 0) && ((ldb & 1) == 0) &&
                          ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
-    // -1 (default): 128x128 tiles for long-k products that fill the machine several times over (2 % faster
-    // there), the 2-CTA/SM 128x64 shape otherwise (rank-k updates, small and skinny products)
+    // -1 (default): pick between 128x128 tiles (cfg 6, one CTA per SM, best asymptote) and 64x64 tiles (cfg 7,
+    // four CTAs per SM: 4x finer tail, shorter pipeline fill) from a two-term cost model fitted to the
+    // measured table in profiles/r01_dgemm_cfg_table.md:  cost = waves * tile_work / (e_inf * k / (k + k0)).
     int cfg = g_dgemm_cfg;
-    if (cfg < 0) cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? (aligned ? 6 : 1) : 0;
+    if (cfg < 0) {
+        if (aligned) {
+            const double t128 = double((m + 127) / 128) * double((n + 127) / 128);
+            const double t64 = double((m + 63) / 64) * double((n + 63) / 64);
+            const double kd = double(k);
+            const double cost128 = ceil(t128 / 148.0) * 4.0 / (0.939 * kd / (kd + 28.0));
+            const double cost64 = ceil(t64 / 148.0) / (0.918 * kd / (kd + 8.0));
+            cfg = cost128 < cost64 ? 6 : 7;
+        } else {
+            cfg = (k >= 2048 && (m / 128) * (n / 128) >= 4 * 148) ? 1 : 0;
+        }
+    }
     if (cfg == 1) {
         return aligned ? launch_cfg<CfgLarge, true>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
                        : launch_cfg<CfgLarge, false>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);

@@ -36,9 +36,9 @@ def main():
     which = sys.argv[1:] or ["dgemm", "sgemm", "lu", "solve"]
     out = []
     if "dgemm" in which or "sgemm" in which:
-        shapes = [(n, n, n) for n in (512, 1024, 2048, 4096, 8192, 16384)] + [(65536, 256, 256), (4096, 32768, 32768), (16384, 256, 16384), (16384, 64, 192)]
+        shapes = [(n, n, n) for n in (256, 512, 1024, 1536, 2048, 4096, 8192, 16384)] + [(65536, 256, 256), (4096, 32768, 32768), (16384, 256, 16384), (16384, 64, 192)]
         for name, dt, fn, cfg in (("dgemm", torch.float64, l.rla_dgemm_dev, 0), ("dgemm", torch.float64, l.rla_dgemm_dev, 1),
-                                  ("dgemm", torch.float64, l.rla_dgemm_dev, 2), ("dgemm", torch.float64, l.rla_dgemm_dev, 5),
+                                  ("dgemm", torch.float64, l.rla_dgemm_dev, 7), ("dgemm", torch.float64, l.rla_dgemm_dev, 5),
                                   ("dgemm", torch.float64, l.rla_dgemm_dev, 6),
                                   ("sgemm", torch.float32, l.rla_sgemm_dev, 0)):
             if name not in which:
