@@ -162,8 +162,9 @@ RLA_API int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *
  *                  U12 = L11^-1 A12 and A22 -= L21 U12 on local columns [c0,c1)
  *   rowid_*      : the row-origin vector every rank carries; perm_from_rowid gives PartialPivLu.p.perm */
 RLA_API size_t rla_lu_plan_bytes(void);
-/* development aid: with rla_set_tuning("lu_dbg", 8) the last panel launch records 64 x 8 globaltimer stamps */
-RLA_API int rla_debug_lu_trace(unsigned long long *host512);
+/* development aid: with rla_set_tuning("lu_dbg", 8) the four inner panels of the last outer block record 64 x 8 words
+ * each (globaltimer stamps in slots 0..6, the pivot row in slot 7); copies 4 x 512 words to host2048 */
+RLA_API int rla_debug_lu_trace(unsigned long long *host2048);
 RLA_API int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w,
                              int32_t *d_info, void *d_plan, void *stream);
 RLA_API int rla_dlu_laswp_dev(double *a_loc, size_t ld, size_t w, const void *d_plan, const int32_t *d_info,
@@ -183,9 +184,10 @@ RLA_API int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size
 RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
                              uint64_t offset, float lo, float scale, void *stream);
 
-/* Tuning knobs (development / benchmarking).  "dgemm_cfg": -1 = auto (default), 0..6 = a fixed CTA shape
+/* Tuning knobs (development / benchmarking).  "dgemm_cfg": -1 = auto (default), 0..7 = a fixed CTA shape
  * (see csrc/dgemm.cu).  "lu_gmax": cap on the panel kernel's row
- * CTAs.  "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
+ * CTAs.  "lu_cluster": 1 (default) = panels that fit one thread-block cluster use the DSMEM panel kernel, 0 = always
+ * the grid-wide kernel.  "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
 RLA_API int rla_set_tuning(const char *key, int value);
 
 /* Diagnostics */

@@ -15,7 +15,7 @@
 namespace rla {
 
 extern int g_dgemm_cfg;   // dgemm.cu
-extern int g_lu_gmax, g_lu_dbg;   // lu.cu
+extern int g_lu_gmax, g_lu_dbg, g_lu_cluster;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 int g_host_gemm_s = 4;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline
 
@@ -654,6 +654,10 @@ int rla_set_tuning(const char *key, int value) {
     }
     if (strcmp(key, "lu_dbg") == 0) {
         g_lu_dbg = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "lu_cluster") == 0) {
+        g_lu_cluster = value ? 1 : 0;
         return RLA_OK;
     }
     return RLA_ERR_INVALID;

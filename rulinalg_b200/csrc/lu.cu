@@ -330,6 +330,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                     *((volatile unsigned long long *)(sc.piv_log + c)) =
                         tag_hi | (sing ? 0xffffffffull : (unsigned long long)(unsigned)gi);
                     if (sing) *info = d + 1; else ipiv[d] = gi;
+                    if (sc.trace) sc.trace[c * 8 + 7] = (unsigned long long)(unsigned)gi;
                 }
             }
         }
@@ -393,6 +394,412 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int r = idx / jb, c = idx - r * jb;
         A[size_t(r0 + r) * ld + J + c] = s[r * PLDS + c];
     }
+}
+
+// -------------------------------------------------------------------------------------------
+// Cluster variant of the panel factorisation, for panels of at most 4096 rows: the whole panel lives in the
+// REGISTERS of one thread-block cluster (<= 16 CTAs x 256 rows; thread (row, half) holds 32 consecutive columns of
+// its row), and the per-column exchange never leaves the SM-to-SM network.  Same arithmetic, same verdicts, same
+// outputs as lu_panel_kernel (bit-identical factors), ~2.5x less latency per column:
+//   * every CTA sends its candidate packet into the `cand` slot it owns in EVERY CTA's shared memory with
+//     st.async (16 tx-bytes completed on the destination's mbarrier when the data has landed); one try_wait later
+//     each CTA holds all candidates locally and reaches the same verdict -- no fence, no L2 round trip;
+//   * rows are never moved: a row's position in the reference's (physically swapped) ordering is a register, the
+//     picked row retires to position J + c and the panel is written back permuted; the two threads that hold a
+//     CTA's candidate row stage it in shared memory BEFORE the packet leaves (CTA barrier in between), everybody
+//     fetches the winner's row with ld.shared::cluster after the verdict.  (A first version staged the row while
+//     the packets were in flight and let readers poll a tag in each 16-byte {value, tag} entry: ~5 % of 4-panel
+//     blocks came out wrong -- a 16-byte DSMEM load is not single-copy atomic against a local 16-byte store.);
+//   * the rank-1 update runs on registers (no shared-memory traffic for the panel); the thread that updates
+//     column c+1 keeps the new value aside: it is the next column's pivot candidate and multiplier numerator.
+//     The column loop is unrolled by 4 so that `c % 4` is static and register indices stay compile-time.
+// Buffers and mbarriers alternate by column parity: a CTA can be at most one column ahead of the slowest one.
+// The hub's duties run after the column loop (16 warps x 128 registers leave no room for extra warps): one warp of
+// CTA rank 0 folds the 64 pivots into the outer block's net-permutation plan while one warp of EVERY CTA folds them
+// into the panel's own net permutation, which all CTAs then apply to the outer block's columns outside the panel as
+// one gather (each CTA a slice of the columns): ~3 us per panel instead of 64 dependent swaps.  No thread exits
+// before the final cluster barrier (remote shared memory must stay alive while anyone may still read it).
+// -------------------------------------------------------------------------------------------
+constexpr int CL_WORKERS = 512;
+constexpr int CL_THREADS = CL_WORKERS;
+constexpr int CL_MAX = 16;
+constexpr int CL_ROWS = CL_WORKERS / 2;                          // rows per CTA
+constexpr int CL_HC = PW / 2;                                    // columns per thread
+constexpr int CL_GC = 16;                                        // columns per pass of the closing gather
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+// remote 16-byte store that completes 16 tx-bytes on the destination CTA's mbarrier when the data has landed
+__device__ __forceinline__ void st_async_v2(unsigned cluster_addr, unsigned long long lo, unsigned long long hi,
+                                            unsigned cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+                 "l"(lo), "l"(hi), "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ double ld_cluster(const double *p, unsigned rank) {
+    unsigned long long v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(mapa(smem_u32(p), rank)) : "memory");
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ float ld_cluster(const float *p, unsigned rank) {
+    unsigned v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(mapa(smem_u32(p), rank)) : "memory");
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void worker_sync() { __syncthreads(); }
+
+// One warp folds the interchange (row d <-> row p) into a net permutation over "touched" rows: index i < w is row
+// base + i, index w + f is far row fr[f]; od[i] / of[f] = touched index whose OLD contents end up there.
+__device__ __forceinline__ void fold_pivot(int *od, int *fr, int *of, int &nf, int base, int w, int d, int p, int lane) {
+    if (p == d) return;
+    const int k = d - base;
+    if (p < base + w) {
+        if (lane == 0) { const int t = od[k]; od[k] = od[p - base]; od[p - base] = t; }
+    } else {
+        int f = -1;
+        for (int b0 = 0; b0 < nf; b0 += 32) {
+            const int q = b0 + lane;
+            const unsigned hit = __ballot_sync(0xffffffffu, q < nf && fr[q] == p);
+            if (hit) { f = b0 + __ffs(hit) - 1; break; }
+        }
+        if (f < 0) {
+            f = nf++;
+            if (lane == 0) { fr[f] = p; of[f] = w + f; }
+        }
+        __syncwarp();
+        if (lane == 0) { const int t = od[k]; od[k] = of[f]; of[f] = t; }
+    }
+    __syncwarp();
+}
+
+// trace stamps without leaving warp 0 diverged (a diverged warp takes the slow BRA.DIV path of redux.sync)
+#define CTRACE(slot)                                                   \
+    do {                                                               \
+        if (sc.trace && rank == 0 && warp == 0) {                      \
+            const unsigned long long t_ = gtime();                     \
+            if (lane == 0) sc.trace[c * 8 + (slot)] = t_;              \
+            __syncwarp();                                              \
+        }                                                              \
+    } while (0)
+
+template <typename T>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+lu_panel_cluster_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32_t *__restrict__ ipiv,
+                        int32_t *__restrict__ info, PanelScratch sc, int J0, int w, int dbg) {
+    if (*info != 0) return;   // written by an earlier kernel => uniform over the cluster
+    extern __shared__ __align__(16) unsigned char panel_smem[];   // [CL_ROWS][PLDS] staging for coalesced panel load / store
+    T *stg = reinterpret_cast<T *>(panel_smem);
+    __shared__ __align__(16) Msg cand[2][CL_MAX];          // [parity][source rank], written remotely (st.async)
+    __shared__ __align__(8) unsigned long long bar[2];     // one mbarrier per parity: 1 arrival (mine) + 16*CS tx-bytes
+    __shared__ __align__(16) T crow[2][PW];                // my candidate row, staged for remote readers
+    __shared__ __align__(16) T prow_s[PW];                 // the pivot row of the current column
+    __shared__ __align__(16) T colv[CL_ROWS];              // column c+1 of my rows (from the half that holds it to the other)
+    __shared__ unsigned long long red_key[CL_WORKERS / 32];
+    __shared__ int red_idx[CL_WORKERS / 32];
+    __shared__ int sh_cpos, sh_idx, sh_win, sh_sing, sh_nt;
+    __shared__ int piv_sm[PW];
+    __shared__ PlanState st;                               // CTA rank 0: the outer block's plan state
+    __shared__ int od_l[PW], fr_l[PW], of_l[PW];           // the panel's own net permutation
+    __shared__ int rows_l[2 * PW], org_l[2 * PW];
+    __shared__ int posv[CL_ROWS];                          // final position of my rows (write-back)
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned rank = cluster_ctarank(), CS = cluster_nctarank();
+    if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 0] = gtime();
+
+    if (tid == 0) {
+        mbar_init(smem_u32(&bar[0]), 1);
+        mbar_init(smem_u32(&bar[1]), 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();
+    if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 1] = gtime();
+
+    // Thread (lrow, half) keeps columns [32*half, 32*half + 32) of one row in registers for the whole panel.  Rows are
+    // never moved: `pos` is the row's current position in the reference's (physically swapped) ordering -- what
+    // ties are broken by and what ipiv records; a picked row goes to position J + c when the panel is written back.
+    const int lrow = tid & (CL_ROWS - 1), half = tid >> 8;
+    const int r0 = J + int(rank) * R;
+    const int nrows = max(0, min(n, r0 + R) - r0);
+    const bool has_row = lrow < nrows;
+    int pos = r0 + lrow;
+    bool active = has_row;                                  // not picked yet
+    T a[CL_HC];
+    for (int idx = tid; idx < nrows * jb; idx += CL_WORKERS) {       // coalesced: 64 consecutive columns per row
+        const int r = idx / jb, cc = idx - r * jb;
+        stg[r * PLDS + cc] = A[size_t(r0 + r) * ld + J + cc];
+    }
+    worker_sync();
+#pragma unroll
+    for (int k = 0; k < CL_HC; ++k) a[k] = (has_row && half * CL_HC + k < jb) ? stg[lrow * PLDS + half * CL_HC + k] : T(0);
+    // the hub's bookkeeping runs inside the column loop, in the shadow of the packet exchange (see below)
+    int nf_l = 0, nf_g = 0;
+    constexpr int LOCAL_FOLD_WARP = CL_WORKERS / 32 - 1, PLAN_FOLD_WARP = CL_WORKERS / 32 - 2;
+    if (warp == LOCAL_FOLD_WARP) {
+        for (int i = lane; i < jb; i += 32) od_l[i] = i;
+    } else if (warp == PLAN_FOLD_WARP && rank == 0) {
+        if (J == J0) {
+            for (int i = lane; i < w; i += 32) st.od[i] = i;
+        } else {
+            for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                st.od[i] = sc.state->od[i];
+                st.fr[i] = sc.state->fr[i];
+                st.of[i] = sc.state->of[i];
+            }
+            nf_g = sc.state->nf;
+        }
+    }
+    if (half == 0) colv[lrow] = a[0];
+    // candidates of column 0 (later columns get theirs from the rank-1 update)
+    {
+        unsigned long long bkey = 0ull;
+        int bidx = INT_MAX;
+        if (active && half == 0) {
+            const T av = fabs(a[0]);
+            if (av == av) { bkey = key_of(double(av)); bidx = pos; }                     // a NaN never wins ...
+            else if (pos == J) { bkey = key_of(CUDART_INF); bidx = pos; }                  // ... unless it is the diagonal
+        }
+        unsigned wm;
+        warp_argmax(bkey, bidx, wm);
+        if (lane == 0) { red_key[warp] = bkey; red_idx[warp] = bidx; }
+    }
+    worker_sync();
+
+    if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 2] = gtime();
+    bool singular = false;
+    for (int c4 = 0; c4 < jb; c4 += 4) {
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {
+            const int c = c4 + s4;
+            if (c >= jb || singular) continue;
+            const int d = J + c;
+            const int par = c & 1;
+            const int rel = c - half * CL_HC;               // column c relative to my 32 (negative: all of mine are right of it)
+            const T colc = colv[lrow];                      // my row's value in column c
+            CTRACE(0);
+            // ---- my CTA's candidate: reduce, stage its row, THEN announce it ----
+            unsigned long long ckey = 0ull;
+            int cidx = INT_MAX;
+            if (warp == 0) {
+                ckey = (lane < CL_WORKERS / 32) ? red_key[lane] : 0ull;
+                cidx = (lane < CL_WORKERS / 32) ? red_idx[lane] : INT_MAX;
+                unsigned wm;
+                warp_argmax(ckey, cidx, wm);
+                if (lane == 0) sh_cpos = cidx;
+            }
+            worker_sync();                                  // A: sh_cpos
+            if (active && pos == sh_cpos && rel < CL_HC) {  // the two threads that hold the candidate row
+#pragma unroll
+                for (int k = 0; k < CL_HC; ++k) crow[par][half * CL_HC + k] = a[k];
+            }
+            worker_sync();                                  // A2: the row is in shared memory before the packet that
+                                                            //     announces it leaves (remote readers fetch it after the verdict)
+            if (warp == 0) {
+                if (lane == 0) mbar_expect_tx(smem_u32(&bar[par]), 16u * CS);
+                __syncwarp();
+                if (unsigned(lane) < CS)
+                    st_async_v2(mapa(smem_u32(&cand[par][rank]), unsigned(lane)), ckey, (unsigned long long)(unsigned)cidx,
+                                mapa(smem_u32(&bar[par]), unsigned(lane)));
+                CTRACE(1);
+            } else if (c > 0) {
+                // while warp 0 waits for the packets: fold the previous pivot into the panel's own net permutation
+                // (every CTA) and into the outer block's plan (CTA 0)
+                if (warp == LOCAL_FOLD_WARP) fold_pivot(od_l, fr_l, of_l, nf_l, J, jb, d - 1, piv_sm[c - 1], lane);
+                else if (warp == PLAN_FOLD_WARP && rank == 0) fold_pivot(st.od, st.fr, st.of, nf_g, J0, w, d - 1, piv_sm[c - 1], lane);
+            }
+            // ---- the verdict: every CTA reduces the same CS packets ----
+            if (warp == 0) {
+                CTRACE(5);
+                mbar_wait(smem_u32(&bar[par]), unsigned(c >> 1) & 1u);
+                CTRACE(6);
+                const int q = min(lane, int(CS) - 1);
+                unsigned long long gk = ((volatile Msg *)&cand[par][q])->lo;
+                int gi = int(unsigned(((volatile Msg *)&cand[par][q])->hi));
+                int gw = q;
+                unsigned wm;
+                warp_argmax(gk, gi, wm);
+                gw = __shfl_sync(0xffffffffu, gw, wm ? __ffs(wm) - 1 : 0);
+                if (lane == 0) {
+                    const int sing = (T(__longlong_as_double((long long)gk)) < Eps<T>::v()) ? 1 : 0;   // lu.rs:179-183
+                    sh_idx = gi;
+                    sh_win = gw;
+                    sh_sing = sing;
+                    piv_sm[c] = gi;
+                    if (rank == 0) {               // CTA 0 keeps the books
+                        if (sing) *info = d + 1; else ipiv[d] = gi;
+                        if (sc.trace) sc.trace[c * 8 + 7] = (unsigned long long)(unsigned)gi;
+                    }
+                }
+            }
+            worker_sync();                                  // B: verdict
+            CTRACE(2);
+            if (sh_sing) { singular = true; continue; }     // uniform over the cluster
+            const int p = sh_idx;                           // position of the pivot row
+            if (tid >= c && tid < jb) prow_s[tid] = ld_cluster(&crow[par][tid], unsigned(sh_win));
+            // bookkeeping of the interchange d <-> p: the picked row retires to position d, the row at d moves to p
+            if (active) {
+                if (pos == p) { active = false; pos = d; }
+                else if (pos == d) pos = p;
+            }
+            worker_sync();                                  // C: pivot row here
+            CTRACE(3);
+            // ---- multiplier (one IEEE division per row, computed by both halves), rank-1 update on registers with
+            //      mul, sub; a[rel] <- m; the new value of column c+1 is kept aside ----
+            T nxt = T(0);
+            if (active && rel < CL_HC) {
+                const T m = div_rn(colc, prow_s[c]);
+                const int gidx = rel >> 2;                  // floor(rel / 4); rel mod 4 == s4
+                const T *u = prow_s + half * CL_HC;
+#pragma unroll
+                for (int gi = 0; gi < CL_HC / 4; ++gi) {
+                    if (gi >= gidx) {                       // warp-uniform
+                        const bool p_gt = gi > gidx, p_eq = gi == gidx;
+#pragma unroll
+                        for (int sub = 0; sub < 4; ++sub) {
+                            const int k = 4 * gi + sub;
+                            const bool act = p_gt || (p_eq && sub > s4);
+                            if (act) a[k] = sub_rn(a[k], mul_rn(m, u[k]));
+                            if (p_eq && sub == s4) a[k] = m;
+                            const bool cap = (s4 < 3) ? (p_eq && sub == s4 + 1) : (gi == gidx + 1 && sub == 0);
+                            if (cap) nxt = a[k];
+                        }
+                    }
+                }
+            }
+            // ---- candidates of column c+1, and its values for the half that does not hold it ----
+            if (c + 1 < jb) {
+                unsigned long long bkey = 0ull;
+                int bidx = INT_MAX;
+                if (half == ((c + 1) >> 5)) {
+                    colv[lrow] = nxt;
+                    if (active) {
+                        const T av = fabs(nxt);
+                        if (av == av) { bkey = key_of(double(av)); bidx = pos; }
+                        else if (pos == d + 1) { bkey = key_of(CUDART_INF); bidx = pos; }     // NaN diagonal stays (lu.rs:170-171)
+                    }
+                }
+                unsigned wm;
+                warp_argmax(bkey, bidx, wm);
+                if (lane == 0) { red_key[warp] = bkey; red_idx[warp] = bidx; }
+            }
+            worker_sync();                                  // E
+            CTRACE(4);
+        }
+    }
+
+    if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 3] = gtime();
+    if (!singular) {
+        // write the panel back permuted: registers -> shared memory -> coalesced rows at their final positions
+        if (has_row) {
+#pragma unroll
+            for (int k = 0; k < CL_HC; ++k) stg[lrow * PLDS + half * CL_HC + k] = a[k];
+            if (half == 0) posv[lrow] = pos;
+        }
+        if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 4] = gtime();
+        // ---- the hub's duties: the last pivot, then publish ----
+        if (warp == PLAN_FOLD_WARP && rank == 0) {
+            // the outer block's net-permutation plan (consumed by rowid_apply_kernel / laswp_apply_kernel)
+            fold_pivot(st.od, st.fr, st.of, nf_g, J0, w, J + jb - 1, piv_sm[jb - 1], lane);
+            if (J + jb != J0 + w) {
+                for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                    sc.state->od[i] = st.od[i];
+                    sc.state->fr[i] = st.fr[i];
+                    sc.state->of[i] = st.of[i];
+                }
+                if (lane == 0) sc.state->nf = nf_g;
+            } else {
+                const int nt = w + nf_g;
+                if (lane == 0) sc.plan->nt = nt;
+                for (int i = lane; i < nt; i += 32) {
+                    sc.plan->rows[i] = (i < w) ? J0 + i : st.fr[i - w];
+                    sc.plan->origin[i] = (i < w) ? st.od[i] : st.of[i - w];
+                }
+            }
+        }
+        if (warp == LOCAL_FOLD_WARP) {
+            // the panel's own net permutation, for the outer block's columns outside the panel
+            fold_pivot(od_l, fr_l, of_l, nf_l, J, jb, J + jb - 1, piv_sm[jb - 1], lane);
+            const int nt = jb + nf_l;
+            for (int i = lane; i < nt; i += 32) {
+                rows_l[i] = (i < jb) ? J + i : fr_l[i - jb];
+                org_l[i] = (i < jb) ? od_l[i] : of_l[i - jb];
+            }
+            if (lane == 0) sh_nt = nt;
+        }
+        worker_sync();
+        for (int idx = tid; idx < nrows * jb; idx += CL_WORKERS) {
+            const int r = idx / jb, cc = idx - r * jb;
+            A[size_t(posv[r]) * ld + J + cc] = stg[r * PLDS + cc];
+        }
+        if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 5] = gtime();
+        if (!(dbg & 1)) {
+            const int na = J - J0, ncols = na + (J0 + w - J - jb);     // columns [J0, J) and [J + jb, J0 + w)
+            const int cpc = (ncols + int(CS) - 1) / int(CS);
+            const int c_lo = int(rank) * cpc, c_hi = min(ncols, c_lo + cpc);
+            const int nt = sh_nt;
+            for (int g0 = c_lo; g0 < c_hi; g0 += CL_GC) {             // uniform per CTA
+                T v[4];
+                bool mv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = tid + CL_WORKERS * u, i = e / CL_GC, t2 = g0 + (e % CL_GC);
+                    mv[u] = i < nt && t2 < c_hi && org_l[i] != i;
+                    if (mv[u]) {
+                        const int col = (t2 < na) ? J0 + t2 : J + jb + (t2 - na);
+                        v[u] = A[size_t(rows_l[org_l[i]]) * ld + col];
+                    }
+                }
+                worker_sync();                                          // every source is read before any destination is written
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int e = tid + CL_WORKERS * u, i = e / CL_GC, t2 = g0 + (e % CL_GC);
+                    if (mv[u]) {
+                        const int col = (t2 < na) ? J0 + t2 : J + jb + (t2 - na);
+                        A[size_t(rows_l[i]) * ld + col] = v[u];
+                    }
+                }
+            }
+        }
+    }
+    if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 6] = gtime();
+    cluster_sync_all();
+    if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 7] = gtime();
 }
 
 // -------------------------------------------------------------------------------------------
@@ -602,6 +1009,7 @@ int g_num_sms = 0;
 unsigned long long *g_lu_trace = nullptr;
 int g_lu_gmax_ref();
 int g_lu_dbg_ref();
+int g_lu_cluster_ref();
 
 // scratch layout (bytes): packets | rowbuf | diagbuf | result | laswp plan | plan state
 constexpr size_t SC_PACKETS = 0;
@@ -667,17 +1075,66 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         attr = true;
     }
+    // largest cluster this device schedules for the cluster panel kernel (16 needs the non-portable opt-in), once
+    static int cluster_max = -1;
+    if (cluster_max < 0) {
+        cluster_max = 0;
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(CL_ROWS) * PLDS * sizeof(T))));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        for (int cs = CL_MAX; cs >= 2; cs /= 2) {
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(cs);
+            cfg.blockDim = dim3(CL_THREADS);
+            cfg.dynamicSmemBytes = size_t(CL_ROWS) * PLDS * sizeof(T);
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = unsigned(cs);
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int nclusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&nclusters, lu_panel_cluster_kernel<T>, &cfg) == cudaSuccess && nclusters > 0) {
+                cluster_max = cs;
+                break;
+            }
+            (void)cudaGetLastError();
+        }
+    }
     PanelScratch sc = scratch_view(ws);
     sc.plan = plan;
     if (g_lu_dbg_ref() & 8) {
         static unsigned long long *trace = nullptr;
-        if (!trace) RLA_CUDA(cudaMalloc(&trace, 64 * 8 * sizeof(unsigned long long)));
+        if (!trace) RLA_CUDA(cudaMalloc(&trace, 4 * 64 * 8 * sizeof(unsigned long long)));
         sc.trace = trace;
         g_lu_trace = trace;
     }
+    unsigned long long *const trace_base = sc.trace;
     for (int j = J0; j < J0 + w; j += PW) {
         const int jb = min(PW, J0 + w - j);
         const int nrem = n - j;
+        if (trace_base) sc.trace = trace_base + size_t((j - J0) / PW) * 64 * 8;   // one page per inner panel
+        // panels of <= 16 x 256 rows: one thread-block cluster, panel in registers, exchange over DSMEM
+        if (g_lu_cluster_ref() && nrem <= cluster_max * CL_ROWS) {
+            int CS = 1;
+            while (CS * CL_ROWS < nrem) CS *= 2;
+            const int R = (nrem + CS - 1) / CS;
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(CS);
+            cfg.blockDim = dim3(CL_THREADS);
+            cfg.dynamicSmemBytes = size_t(CL_ROWS) * PLDS * sizeof(T);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = unsigned(CS);
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            RLA_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<T>, a, ld, n, j, jb, R, ipiv, d_info, sc, J0, w,
+                                        g_lu_dbg_ref()));
+            note_launch();
+        } else {
         int G = min(min(g_num_sms - 1, g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
         while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
         int R = (nrem + G - 1) / G;
@@ -695,6 +1152,7 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
             RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, s));
             note_launch();
             ws.tag += unsigned(jb);
+        }
         }
         // U12 and the Schur update inside the outer block
         if (j + jb < J0 + w) {
@@ -751,12 +1209,13 @@ int trsm_block(const T *L, size_t ldl, int w, T *B, size_t ldb, int ncols, const
 int g_lu_gmax = 112;          // rla_set_tuning("lu_gmax", v): cap on the panel kernel's row CTAs (112: leaves SMs whole for
                               // the overlapped Schur update; measured 1-5 % faster than 147 at n >= 16384)
 int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bit0: hub skips row swaps, bit2: no look-ahead)
-namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } }
+int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", 0/1): panels that fit one thread-block cluster use the DSMEM kernel
+namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } }
 
 size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
 int lu_trace_fetch(unsigned long long *host512) {
     if (!g_lu_trace) return RLA_ERR_INVALID;
-    RLA_CUDA(cudaMemcpy(host512, g_lu_trace, 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    RLA_CUDA(cudaMemcpy(host512, g_lu_trace, 4 * 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
     return RLA_OK;
 }
 
