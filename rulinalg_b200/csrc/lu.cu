@@ -561,9 +561,15 @@ lu_panel_cluster_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int 
     int pos = r0 + lrow;
     bool active = has_row;                                  // not picked yet
     T a[CL_HC];
-    for (int idx = tid; idx < nrows * jb; idx += CL_WORKERS) {       // coalesced: 64 consecutive columns per row
-        const int r = idx / jb, cc = idx - r * jb;
-        stg[r * PLDS + cc] = A[size_t(r0 + r) * ld + J + cc];
+    if (jb == PW) {
+#pragma unroll 8
+        for (int idx = tid; idx < nrows * PW; idx += CL_WORKERS)          // coalesced: 64 consecutive columns per row
+            stg[(idx >> 6) * PLDS + (idx & 63)] = A[size_t(r0 + (idx >> 6)) * ld + J + (idx & 63)];
+    } else {
+        for (int idx = tid; idx < nrows * jb; idx += CL_WORKERS) {
+            const int r = idx / jb, cc = idx - r * jb;
+            stg[r * PLDS + cc] = A[size_t(r0 + r) * ld + J + cc];
+        }
     }
     worker_sync();
 #pragma unroll
@@ -763,9 +769,15 @@ lu_panel_cluster_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int 
             if (lane == 0) sh_nt = nt;
         }
         worker_sync();
-        for (int idx = tid; idx < nrows * jb; idx += CL_WORKERS) {
-            const int r = idx / jb, cc = idx - r * jb;
-            A[size_t(posv[r]) * ld + J + cc] = stg[r * PLDS + cc];
+        if (jb == PW) {
+#pragma unroll 8
+            for (int idx = tid; idx < nrows * PW; idx += CL_WORKERS)
+                A[size_t(posv[idx >> 6]) * ld + J + (idx & 63)] = stg[(idx >> 6) * PLDS + (idx & 63)];
+        } else {
+            for (int idx = tid; idx < nrows * jb; idx += CL_WORKERS) {
+                const int r = idx / jb, cc = idx - r * jb;
+                A[size_t(posv[r]) * ld + J + cc] = stg[r * PLDS + cc];
+            }
         }
         if (sc.trace && rank == 0 && tid == 0 && w == PW) sc.trace[1536 + 5] = gtime();
         if (!(dbg & 1)) {

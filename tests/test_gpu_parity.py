@@ -348,6 +348,52 @@ def test_lu_pivot_rule_ties_and_nan(rla, oracle):
     assert np.array_equal(f.lu.to_numpy(), ref_lu, equal_nan=True)
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_lu_cluster_panel_identical_to_grid_panel(rla, oracle, dtype):
+    """The two panel kernels (grid-wide exchange through L2; one thread-block cluster with the panel in registers and
+    the exchange over DSMEM) must produce bit-identical factors, permutations and status: same pivot rule
+    (lu.rs:170-178), same unfused arithmetic.  Sizes cover 1/2/4/8/16-CTA clusters, ragged last panels, the hand-over
+    from the grid kernel (n > 4096), ties, a NaN diagonal and a singular matrix."""
+    import torch
+    l = rla.lib()
+    tdt = torch.float64 if dtype == np.float64 else torch.float32
+    fn = l.rla_dgetrf_dev if dtype == np.float64 else l.rla_sgetrf_dev
+    s = torch.cuda.current_stream().cuda_stream
+
+    def factor(a_np, mode):
+        assert l.rla_set_tuning(b"lu_cluster", mode) == 0
+        n = a_np.shape[0]
+        a = torch.from_numpy(a_np.copy()).cuda()
+        perm = torch.empty(n, dtype=torch.int64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        rla.check(fn(n, a.data_ptr(), n, perm.data_ptr(), info.data_ptr(), s))
+        torch.cuda.synchronize()
+        return a.cpu().numpy(), perm.cpu().numpy(), int(info.item())
+
+    try:
+        cases = []
+        for n in (5, 64, 65, 200, 257, 300, 777, 1030, 2100, 4096, 4500):
+            cases.append(oracle.fill_uniform((n, n), 700 + n, dtype, lo=-0.5, scale=1.0))
+        ties = oracle.fill_uniform((600, 600), 11, dtype, lo=-0.5, scale=1.0)
+        ties[:, 0] = 0.25                       # every row ties in column 0: the first one must win in both kernels
+        ties[300:, 3] = ties[:300, 3]           # ties between rows that live in different CTAs
+        cases.append(ties)
+        nan_diag = oracle.fill_uniform((300, 300), 12, dtype, lo=-0.5, scale=1.0)
+        nan_diag[0, 0] = np.nan                 # a NaN diagonal stays the pivot (lu.rs:170-171)
+        cases.append(nan_diag)
+        sing = oracle.fill_uniform((400, 400), 13, dtype, lo=-0.5, scale=1.0)
+        sing[:, 130] = 0.0                      # exact zero column -> DivByZero at column 130 in both kernels
+        cases.append(sing)
+        for a in cases:
+            g, c = factor(a, 0), factor(a, 1)
+            assert g[2] == c[2]
+            if g[2] == 0:
+                assert np.array_equal(g[1], c[1])
+                assert np.array_equal(g[0], c[0], equal_nan=True)
+    finally:
+        l.rla_set_tuning(b"lu_cluster", 1)
+
+
 def lu_checks(rla, oracle, a, f, ref=None):
     n = a.shape[0]
     dt = a.dtype
