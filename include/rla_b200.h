@@ -187,7 +187,8 @@ RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_
 /* Tuning knobs (development / benchmarking).  "dgemm_cfg": -1 = auto (default), 0..7 = a fixed CTA shape
  * (see csrc/dgemm.cu).  "lu_gmax": cap on the panel kernel's row
  * CTAs.  "lu_cluster": 1 (default) = panels that fit one thread-block cluster use the DSMEM panel kernel, 0 = always
- * the grid-wide kernel.  "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
+ * the grid-wide kernel.  "host_gemm_2d": 1 (default) = 2-D wavefront pipeline for large host-pointer products, 0 = row panels;
+ * "host_gemm_s": strips per dimension of that pipeline, 0 (default) = auto.  "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
 RLA_API int rla_set_tuning(const char *key, int value);
 
 /* Diagnostics */

@@ -17,7 +17,7 @@ namespace rla {
 extern int g_dgemm_cfg;   // dgemm.cu
 extern int g_lu_gmax, g_lu_dbg, g_lu_cluster;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
-int g_host_gemm_s = 4;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline
+int g_host_gemm_s = 0;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline; 0 = auto (~512-row strips)
 
 namespace {
 
@@ -61,6 +61,7 @@ struct Context {
     bool ready = false;
     int device = -1;
     cudaStream_t stream = nullptr;       // compute
+    cudaStream_t stream2 = nullptr;      // second compute stream (column strips of the host GEMM pipeline)
     cudaStream_t copy_in = nullptr;      // H2D
     cudaStream_t copy_out = nullptr;     // D2H
     Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync, dTrsv;
@@ -103,6 +104,7 @@ int ensure_ctx(int device = -1) {
     if (prop.major != 10) return RLA_ERR_NO_DEVICE;   // kernels are sm_100a only; no fallback
     RLA_CUDA(cudaSetDevice(device));
     if (!c.stream) RLA_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
+    if (!c.stream2) RLA_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
     if (!c.copy_in) RLA_CUDA(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
     if (!c.copy_out) RLA_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
     c.device = device;
@@ -192,11 +194,15 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         // [0..s-1] x s) and downloads it.  Work availability grows quadratically while uploads proceed linearly,
         // so the kernel starts after 2/S of the H2D traffic instead of after all of B, and PCIe in both
         // directions stays busy under the DMMA kernel.
-        const size_t S = size_t(g_host_gemm_s);
+        size_t S = size_t(g_host_gemm_s);
+        if (S == 0) {                    // measured at n = 8192 (tools/e2e_probe.py): 45 / 40 / 38.4 / 38.8 ms for S = 4 / 8 / 16 / 32
+            S = (m > n ? m : n) / 512;
+            S = S < 4 ? 4 : (S > 32 ? 32 : S);
+        }
         const size_t pm = ((m + S - 1) / S + 127) / 128 * 128, pn = ((n + S - 1) / S + 127) / 128 * 128;
         const size_t sm = (m + pm - 1) / pm, sn = (n + pn - 1) / pn;
         const size_t steps = sm > sn ? sm : sn;
-        while (cx.events.size() < 2 * steps + 1) {
+        while (cx.events.size() < 3 * steps + 1) {
             cudaEvent_t e;
             RLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             cx.events.push_back(e);
@@ -207,22 +213,29 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
             const size_t cols = st < sn ? (c0 + pn <= n ? pn : n - c0) : 0;
             if (rows) RLA_TRY(upload_matrix(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, cx.copy_in));
             if (cols) RLA_TRY(upload_matrix(dB + c0, ldb, hb + c0, hrsb, k, cols, cx.copy_in));
-            RLA_CUDA(cudaEventRecord(cx.events[2 * st], cx.copy_in));
-            RLA_CUDA(cudaStreamWaitEvent(cx.stream, cx.events[2 * st], 0));
-            // row strip: rows of panel st against every chunk uploaded so far (including this step's)
+            cudaEvent_t ev_in = cx.events[3 * st], ev_row = cx.events[3 * st + 1], ev_col = cx.events[3 * st + 2];
+            RLA_CUDA(cudaEventRecord(ev_in, cx.copy_in));
+            // row strip: rows of panel st against every chunk uploaded so far (including this step's);
+            // column strip: panels before st against this step's chunk.  The two strips write disjoint tiles of C and
+            // run on two streams, so the partial last wave of one is filled by the other (and by the next step's).
             const size_t ncols_avail = (st + 1 < sn ? (st + 1) * pn : n);
-            // column strip: panels before st against this step's chunk
             const size_t nrows_prev = (st < sm ? st * pm : m);
-            // launch the larger strip first so its download overlaps the smaller strip's kernel
-            if (rows) RLA_TRY(gemm_dev<T>(rows, k, ncols_avail, alpha, dA + r0 * lda, lda, dB, ldb, beta, dC + r0 * ldc, ldc, cx.stream));
-            RLA_CUDA(cudaEventRecord(cx.events[2 * st + 1], cx.stream));
-            RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * st + 1], 0));
-            if (rows) RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, ncols_avail, cx.copy_out));
+            if (rows) {
+                RLA_CUDA(cudaStreamWaitEvent(cx.stream, ev_in, 0));
+                RLA_TRY(gemm_dev<T>(rows, k, ncols_avail, alpha, dA + r0 * lda, lda, dB, ldb, beta, dC + r0 * ldc, ldc, cx.stream));
+                RLA_CUDA(cudaEventRecord(ev_row, cx.stream));
+            }
             if (cols && nrows_prev) {
-                RLA_TRY(gemm_dev<T>(nrows_prev, k, cols, alpha, dA, lda, dB + c0, ldb, beta, dC + c0, ldc, cx.stream));
-                // reuse the input event slot of this step for the second strip's completion
-                RLA_CUDA(cudaEventRecord(cx.events[2 * st], cx.stream));
-                RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * st], 0));
+                RLA_CUDA(cudaStreamWaitEvent(cx.stream2, ev_in, 0));
+                RLA_TRY(gemm_dev<T>(nrows_prev, k, cols, alpha, dA, lda, dB + c0, ldb, beta, dC + c0, ldc, cx.stream2));
+                RLA_CUDA(cudaEventRecord(ev_col, cx.stream2));
+            }
+            if (rows) {
+                RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, ev_row, 0));
+                RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, ncols_avail, cx.copy_out));
+            }
+            if (cols && nrows_prev) {
+                RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, ev_col, 0));
                 RLA_TRY(download_matrix(hc + c0, hrsc, dC + c0, ldc, nrows_prev, cols, cx.copy_out));
             }
         }
@@ -255,6 +268,7 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
     }
     RLA_CUDA(cudaStreamSynchronize(cx.copy_out));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream2));
     if (!c_direct)
         for (size_t i = 0; i < m; ++i)
             for (size_t j = 0; j < n; ++j) c[ptrdiff_t(i) * rsc + ptrdiff_t(j) * csc] = pc[i * n + j];
@@ -644,7 +658,7 @@ int rla_set_tuning(const char *key, int value) {
         return RLA_OK;
     }
     if (strcmp(key, "host_gemm_s") == 0) {
-        if (value < 1 || value > 64) return RLA_ERR_INVALID;
+        if (value < 0 || value > 64) return RLA_ERR_INVALID;
         g_host_gemm_s = value;
         return RLA_OK;
     }
