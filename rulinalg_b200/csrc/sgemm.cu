@@ -99,24 +99,31 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     const float *b_src = B + size_t(b_row) * ldb + (b_gn < N ? b_gn : 0);
     const int b_bytes_full = b_gn + 3 < N ? 16 : (b_gn < N ? (N - b_gn) * 4 : 0);
 
+    // The slab pointers advance by constant strides (64-bit adds): base + k0 arithmetic compiles to IMAD.WIDE / IMAD,
+    // which execute on the same FMA pipe the FFMA2s need (ncu: ~15 per slab per warp, with pipe-throttle stalls).
+    const float *pa0 = a_src0, *pa1 = a_src1;                 // slab being loaded: A columns k0 + a_kq ..
+    const float *pb = b_src;                                  //                    B rows k0 + b_row (+8)
+    const size_t b_step = size_t(BK) * ldb, b_half = size_t(8) * ldb;
     auto load_a = [&](int k0, float4 &r0, float4 &r1) {
         r0 = make_float4(0.f, 0.f, 0.f, 0.f);
         r1 = r0;
         const int gk = k0 + a_kq;
         if (ALIGNED && gk + 3 < K) {
-            if (a_ok0) r0 = *reinterpret_cast<const float4 *>(a_src0 + k0);
-            if (a_ok1) r1 = *reinterpret_cast<const float4 *>(a_src1 + k0);
+            if (a_ok0) r0 = *reinterpret_cast<const float4 *>(pa0);
+            if (a_ok1) r1 = *reinterpret_cast<const float4 *>(pa1);
         } else {
             float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 if (gk + q < K) {
-                    if (a_ok0) t0[q] = a_src0[k0 + q];
-                    if (a_ok1) t1[q] = a_src1[k0 + q];
+                    if (a_ok0) t0[q] = pa0[q];
+                    if (a_ok1) t1[q] = pa1[q];
                 }
             r0 = make_float4(t0[0], t0[1], t0[2], t0[3]);
             r1 = make_float4(t1[0], t1[1], t1[2], t1[3]);
         }
+        pa0 += BK;
+        pa1 += BK;
     };
     auto store_a = [&](float *as, const float4 &r0, const float4 &r1) {
         float *p = as + a_kq * LDT + a_row;
@@ -130,7 +137,7 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
             const bool ok = k0 + row < K;
             if (ALIGNED) {
                 const int bytes = ok ? b_bytes_full : 0;
-                cp_async16(smem_u32(bs + row * LDT + b_c4), bytes ? b_src + size_t(k0 + 8 * i) * ldb : B, bytes);
+                cp_async16(smem_u32(bs + row * LDT + b_c4), bytes ? (i ? pb + b_half : pb) : B, bytes);
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -139,6 +146,7 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
                 }
             }
         }
+        pb += b_step;
     };
 
     unsigned long long acc[8][4];          // acc[i][j2] = (C[i][2*j2], C[i][2*j2+1])
@@ -160,13 +168,13 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
 
     for (int kt = 0; kt < KT; ++kt) {
         const int s = kt & 1;
-        const float *ap = As + s * TILE + ty * 4;
-        const float *bp = Bs + s * TILE + tx * 4;
+        const float *ap = (s ? As + TILE : As) + ty * 4;
+        const float *bp = (s ? Bs + TILE : Bs) + tx * 4;
         const bool more = kt + 1 < KT;
         float4 r0, r1;
         if (more) {                         // slab kt+1: A parked in registers, B by cp.async into the other stage
             load_a((kt + 1) * BK, r0, r1);
-            copy_b(Bs + (s ^ 1) * TILE, (kt + 1) * BK);
+            copy_b(s ? Bs : Bs + TILE, (kt + 1) * BK);
             cp_async_commit();
         }
         Frag f[2];
@@ -177,7 +185,7 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
             mma_frag(acc, f[kk & 1]);
         }
         if (more) {
-            store_a(As + (s ^ 1) * TILE, r0, r1);
+            store_a(s ? As : As + TILE, r0, r1);
             cp_async_wait<0>();
         }
         __syncthreads();
