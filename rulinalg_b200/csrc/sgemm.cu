@@ -172,17 +172,20 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
         const float *bp = (s ? Bs + TILE : Bs) + tx * 4;
         const bool more = kt + 1 < KT;
         float4 r0, r1;
-        if (more) {                         // slab kt+1: A parked in registers, B by cp.async into the other stage
-            load_a((kt + 1) * BK, r0, r1);
-            copy_b(s ? Bs : Bs + TILE, (kt + 1) * BK);
-            cp_async_commit();
-        }
         Frag f[2];
         load_frag(f[0], ap, bp, 0);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
             if (kk + 1 < BK) load_frag(f[(kk + 1) & 1], ap, bp, kk + 1);
             mma_frag(acc, f[kk & 1]);
+            // slab kt+1 (A parked in registers, B by cp.async into the other stage) is requested AFTER the first k-step's
+            // FFMA2s are in the pipe: right after the barrier every warp of the CTA would otherwise run ~100 address /
+            // predicate / copy-issue instructions with the FMA pipe idle (same fix as in the DGEMM kernel)
+            if (kk == 0 && more) {
+                load_a((kt + 1) * BK, r0, r1);
+                copy_b(s ? Bs : Bs + TILE, (kt + 1) * BK);
+                cp_async_commit();
+            }
         }
         if (more) {
             store_a(s ? As : As + TILE, r0, r1);
