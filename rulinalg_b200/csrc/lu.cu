@@ -1218,8 +1218,9 @@ int trsm_block(const T *L, size_t ldl, int w, T *B, size_t ldb, int ncols, const
 
 }  // namespace
 
-int g_lu_gmax = 112;          // rla_set_tuning("lu_gmax", v): cap on the panel kernel's row CTAs (112: leaves SMs whole for
-                              // the overlapped Schur update; measured 1-5 % faster than 147 at n >= 16384)
+int g_lu_gmax = 32;           // rla_set_tuning("lu_gmax", v): cap on the grid panel kernel's row CTAs (raised automatically until the
+                              // rows fit in shared memory).  The panel is latency-bound, its CTAs only take SMs from the overlapped
+                              // Schur update: tools/lu_gmax_sweep.py, n = 16384: 120.9 / 128.0 / 133.1 ms at 32 / 112 / 147
 int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bit0: hub skips row swaps, bit2: no look-ahead)
 int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", 0/1): panels that fit one thread-block cluster use the DSMEM kernel
 namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } }
