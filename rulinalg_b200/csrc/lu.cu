@@ -13,14 +13,19 @@
 //     round differently (tolerance stated in DESIGN.md / tests).
 //
 // Structure (two-level): outer block W=256 columns, inner panels PW=64 columns.
-//   panel  : lu_panel_kernel   -- cooperative launch, <=1 CTA per SM, each CTA keeps its rows of the
-//                                 panel in shared memory; per column ONE grid-wide barrier: CTAs post
-//                                 (|max|, row, row contents), everyone reduces the posted candidates.
-//   laswp  : laswp_kernel      -- applies a block of row interchanges as ONE gather (net permutation
-//                                 computed by a warp with ballot search) instead of jb dependent swaps;
-//                                 also carries the row-origin vector from which `perm` is produced.
-//   trsm   : trsm_unit_lower_kernel -- U12 = L11^-1 A12, thread per column, column in registers.
+//   panel  : lu_panel_kernel          -- tall panels: cooperative launch of G row CTAs (+1 hub CTA), each CTA keeps its rows
+//                                        of the panel in shared memory; per column ONE grid-wide exchange of 16-byte
+//                                        self-validating messages through L2, every CTA reduces the posted candidates.
+//            lu_panel_cluster_kernel  -- panels of <= 4096 rows: one thread-block cluster (<= 16 CTAs), panel in registers,
+//                                        candidates exchanged with st.async + mbarrier over DSMEM, implicit pivoting.
+//                                        Bit-identical to lu_panel_kernel.
+//   laswp  : laswp_apply_kernel       -- applies an outer block's row interchanges as ONE gather (net permutation "plan"
+//                                        built incrementally by the panel kernels) instead of 256 dependent swaps;
+//                                        rowid_apply_kernel carries the row-origin vector from which `perm` is produced.
+//   trsm   : trsm_unit_lower_kernel   -- U12 = L11^-1 A12, four threads per column, column in registers.
 //   gemm   : dgemm_launch / sgemm_launch (alpha=-1, beta=1) for the Schur complement.
+//   driver : getrf_launch             -- depth-1 look-ahead: block k+1 is factored on a high-priority side stream while
+//                                        the rank-256 update of block k runs on the caller's stream.
 #include <cfloat>
 #include <climits>
 #include <math_constants.h>
