@@ -35,6 +35,7 @@ extern "C" {
 #define RLA_OK 0
 #define RLA_ERR_SINGULAR 1      /* |pivot| < epsilon  -> ErrorKind::DivByZero                */
 #define RLA_ERR_INVALID 2       /* bad argument (negative stride on an output, null pointer) */
+#define RLA_ERR_NOT_POSITIVE 3  /* Cholesky: a diagonal entry is negative (ErrorKind::DecompFailure)      */
 #define RLA_ERR_CUDA (-1)       /* a CUDA call failed; see rla_last_cuda_error()             */
 #define RLA_ERR_NOMEM (-2)      /* device or pinned-host allocation failed                   */
 #define RLA_ERR_NO_DEVICE (-3)  /* no sm_100 device visible (there is no CPU fallback)       */
@@ -85,6 +86,26 @@ RLA_API int rla_sgetrs(size_t n, const float *lu, const size_t *perm, float *b);
  * written in full.  RLA_ERR_SINGULAR when some |u_ii| < epsilon (back_substitution's test, mod.rs:333-336). */
 RLA_API int rla_dgetri(size_t n, const double *lu, const size_t *perm, double *inv);
 RLA_API int rla_sgetri(size_t n, const float *lu, const size_t *perm, float *inv);
+
+/* Cholesky::{decompose, solve, inverse} (src/matrix/decomposition/cholesky.rs:116-233) -- SURVEY 8f "next" row.
+ * rla_?potrf: `a` is n x n row-major contiguous; on return its LOWER triangle holds L with A = L L^T (the reference's
+ * `Cholesky.l`); only the lower triangle of the input is read; the strict upper triangle is unspecified on return
+ * (`unpack` zeroes it, cholesky.rs:237-245).  RLA_ERR_SINGULAR <-> DecompFailure("Matrix is singular to working
+ * precision."), RLA_ERR_NOT_POSITIVE <-> DecompFailure("Diagonal entries of matrix are not all positive.")
+ * (cholesky.rs:151-158).  n <= 64 is bit-identical to the reference; larger n is a blocked right-looking factorisation
+ * on the GEMM kernels.  rla_?potrs: b <- A^-1 b (forward_substitution + transpose_back_substitution, :194-203, :329-365);
+ * RLA_ERR_SINGULAR when some |l_ii| < epsilon.  rla_?potri: inv (n x n contiguous) <- A^-1 (:209-233). */
+RLA_API int rla_dpotrf(size_t n, double *a);
+RLA_API int rla_spotrf(size_t n, float *a);
+RLA_API int rla_dpotrs(size_t n, const double *l, double *b);
+RLA_API int rla_spotrs(size_t n, const float *l, float *b);
+RLA_API int rla_dpotri(size_t n, const double *l, double *inv);
+RLA_API int rla_spotri(size_t n, const float *l, float *inv);
+/* device-resident factorisation: a (row stride ld) in place; ws: rla_potrf_workspace_bytes(n, sizeof(T)) bytes of device
+ * scratch; *d_info <- 0, j+1 (singular at column j) or -(j+1) (negative diagonal at column j); asynchronous on `stream` */
+RLA_API size_t rla_potrf_workspace_bytes(size_t n, size_t elem_size);
+RLA_API int rla_dpotrf_dev(size_t n, double *a, size_t ld, void *ws, int32_t *d_info, void *stream);
+RLA_API int rla_spotrf_dev(size_t n, float *a, size_t ld, void *ws, int32_t *d_info, void *stream);
 
 /* solve_l_triangular / solve_u_triangular (src/matrix/base/mod.rs:1015-1067 -> forward_substitution /
  * back_substitution, src/matrix/mod.rs:318-398) -- SURVEY 8f.  `a` is n x n row-major with row stride rs (only the

@@ -69,6 +69,14 @@ def _lib(fast: bool = False):
         getattr(lib, f"orc_{pre}lu_forward_substitution").restype = None
         getattr(lib, f"orc_{pre}back_substitution").argtypes = [sz, P, sz, P]
         getattr(lib, f"orc_{pre}forward_substitution").argtypes = [sz, P, sz, P]
+    for pre in ("d", "s"):
+        getattr(lib, f"orc_{pre}potrf").argtypes = [sz, P]
+        getattr(lib, f"orc_{pre}potrf").restype = C.c_long
+        getattr(lib, f"orc_{pre}potrs").argtypes = [sz, P, P]
+        getattr(lib, f"orc_{pre}transpose_back_substitution").argtypes = [sz, P, sz, P]
+    lib.orc_dpotri.argtypes = [sz, P, P]
+    lib.orc_dpotrf_det.argtypes = [sz, P]
+    lib.orc_dpotrf_det.restype = dbl
     lib.orc_dgetri.argtypes = [sz, P, P, P]
     lib.orc_perm_sign.argtypes = [sz, P]
     lib.orc_ddet.argtypes = [sz, P, P]
@@ -248,6 +256,64 @@ def lu_unpack(lu: np.ndarray):
     u = np.empty((n, n))
     _lib().orc_dunpack(n, _p(lu), _p(l), _p(u))
     return l, u
+
+
+# ----------------------------------------------------------------------------- Cholesky
+class DecompFailure(Exception):
+    """Mirror of ErrorKind::DecompFailure (src/error.rs)."""
+
+
+def cholesky_decompose(a: np.ndarray, fast: bool = False) -> np.ndarray:
+    """Cholesky::decompose (cholesky.rs:116-170): returns the packed factor (lower triangle = L, strict upper triangle =
+    the input's, untouched); raises DecompFailure with the reference's two messages."""
+    assert a.ndim == 2 and a.shape[0] == a.shape[1], "Matrix must be square for Cholesky decomposition."
+    l = np.array(a, order="C", copy=True)
+    rc = getattr(_lib(fast), f"orc_{_pre(l.dtype)}potrf")(l.shape[0], _p(l))
+    if rc > 0:
+        raise DecompFailure("Matrix is singular to working precision.")
+    if rc < 0:
+        raise DecompFailure("Diagonal entries of matrix are not all positive.")
+    return l
+
+
+def cholesky_unpack(l: np.ndarray) -> np.ndarray:
+    """Decomposition::unpack (cholesky.rs:237-245): zero the strict upper triangle."""
+    return np.tril(l)
+
+
+def cholesky_solve(l: np.ndarray, b: np.ndarray, fast: bool = False) -> np.ndarray:
+    l = np.ascontiguousarray(l)
+    n = l.shape[0]
+    assert b.size == n, "RHS vector and coefficient matrix must be dimensionally compatible."
+    x = np.array(b, dtype=l.dtype, copy=True).reshape(n)
+    rc = getattr(_lib(fast), f"orc_{_pre(l.dtype)}potrs")(n, _p(l), _p(x))
+    if rc != ORC_OK:
+        raise DivByZero("Matrix L is singular to working precision.")
+    return x
+
+
+def transpose_back_substitution(l: np.ndarray, y: np.ndarray) -> np.ndarray:
+    l = np.ascontiguousarray(l)
+    x = np.array(y, dtype=l.dtype, copy=True)
+    rc = getattr(_lib(), f"orc_{_pre(l.dtype)}transpose_back_substitution")(l.shape[0], _p(l), l.shape[1], _p(x))
+    if rc != ORC_OK:
+        raise DivByZero("Matrix L is singular to working precision.")
+    return x
+
+
+def cholesky_inverse(l: np.ndarray) -> np.ndarray:
+    l = np.ascontiguousarray(l, dtype=np.float64)
+    n = l.shape[0]
+    inv = np.zeros((n, n))
+    rc = _lib().orc_dpotri(n, _p(l), _p(inv))
+    if rc != ORC_OK:
+        raise DivByZero("Matrix L is singular to working precision.")
+    return inv
+
+
+def cholesky_det(l: np.ndarray) -> float:
+    l = np.ascontiguousarray(l, dtype=np.float64)
+    return _lib().orc_dpotrf_det(l.shape[0], _p(l))
 
 
 def perm_as_matrix(perm: np.ndarray) -> np.ndarray:

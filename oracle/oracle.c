@@ -321,6 +321,89 @@ int orc_dgetri(size_t n, const double *lu, const size_t *perm, double *inv) {
     return ORC_OK;
 }
 
+/* ------------------------------------------------------------------------------------------
+ * Cholesky: src/matrix/decomposition/cholesky.rs.
+ *   decompose (:116-170): "gaxpy-rich" left-looking, column j:  for k in j..n:
+ *       a_kj = a_kj - utils::dot(a[k,0..j], a[j,0..j]);  d = a_jj;  |d| < eps -> DecompFailure
+ *       ("Matrix is singular to working precision."), d < 0 -> DecompFailure ("Diagonal entries of
+ *       matrix are not all positive.");  a_kj = a_kj / sqrt(d) for k in j..n.
+ *       Only the lower triangle is read or written; the strict upper triangle keeps the input.
+ *   returns 0, +(j+1) for the singular case at column j, -(j+1) for the negative case.
+ *   solve (:194-203): forward_substitution (mod.rs:363-398) then transpose_back_substitution
+ *       (:329-365): for i descending: |l_ii| < eps -> DivByZero; x_i = x_i / l_ii;
+ *       x_j = x_j - x_i * l_ij for j < i (separate mul, sub).
+ *   det (:175-180): fold(one, a*b) over the diagonal, squared.   inverse (:209-233): n solves.
+ * ---------------------------------------------------------------------------------------- */
+#define DEFINE_POTRF(NAME, T, EPS, FABS, SQRT, DOT)                                            \
+long NAME(size_t n, T *a)                                                                      \
+{                                                                                              \
+    for (size_t j = 0; j < n; ++j) {                                                           \
+        if (j > 0) {                                                                           \
+            for (size_t k = j; k < n; ++k) {                                                   \
+                T kj_dot = DOT(a + k * n, a + j * n, j);                                       \
+                a[k * n + j] = a[k * n + j] - kj_dot;                                          \
+            }                                                                                  \
+        }                                                                                      \
+        T diagonal = a[j * n + j];                                                             \
+        if (FABS(diagonal) < EPS) return (long)(j + 1);                                        \
+        else if (diagonal < (T)0) return -(long)(j + 1);                                       \
+        T divisor = SQRT(diagonal);                                                            \
+        for (size_t k = j; k < n; ++k) a[k * n + j] = a[k * n + j] / divisor;                  \
+    }                                                                                          \
+    return 0;                                                                                  \
+}
+DEFINE_POTRF(orc_dpotrf, double, DBL_EPSILON, fabs, sqrt, orc_ddot)
+DEFINE_POTRF(orc_spotrf, float, FLT_EPSILON, fabsf, sqrtf, orc_sdot)
+
+#define DEFINE_TBACK(NAME, T, EPS, FABS)                                                       \
+int NAME(size_t n, const T *l, size_t rs, T *x)                                                \
+{                                                                                              \
+    for (size_t i = n; i-- > 0;) {                                                             \
+        const T *row = l + i * rs;                                                             \
+        T diagonal = row[i];                                                                   \
+        if (FABS(diagonal) < EPS) return ORC_ERR_SINGULAR;                                     \
+        x[i] = x[i] / diagonal;                                                                \
+        for (size_t j = 0; j < i; ++j) {                                                       \
+            T prod = x[i] * row[j];                                                            \
+            x[j] = x[j] - prod;                                                                \
+        }                                                                                      \
+    }                                                                                          \
+    return ORC_OK;                                                                             \
+}
+DEFINE_TBACK(orc_dtranspose_back_substitution, double, DBL_EPSILON, fabs)
+DEFINE_TBACK(orc_stranspose_back_substitution, float, FLT_EPSILON, fabsf)
+
+#define DEFINE_POTRS(NAME, T, FWD, TBACK)                                                      \
+int NAME(size_t n, const T *l, T *b)                                                           \
+{                                                                                              \
+    int st = FWD(n, l, n, b);                                                                  \
+    if (st != ORC_OK) return st;                                                               \
+    return TBACK(n, l, n, b);                                                                  \
+}
+DEFINE_POTRS(orc_dpotrs, double, orc_dforward_substitution, orc_dtranspose_back_substitution)
+DEFINE_POTRS(orc_spotrs, float, orc_sforward_substitution, orc_stranspose_back_substitution)
+
+/* Cholesky::inverse: column i of inv = solve(e_i) */
+int orc_dpotri(size_t n, const double *l, double *inv) {
+    double *e = (double *)malloc(sizeof(double) * (n ? n : 1));
+    for (size_t i = 0; i < n; ++i) {
+        for (size_t j = 0; j < n; ++j) e[j] = 0.0;
+        e[i] = 1.0;
+        int st = orc_dpotrs(n, l, e);
+        if (st != ORC_OK) { free(e); return st; }
+        for (size_t j = 0; j < n; ++j) inv[j * n + i] = e[j];
+    }
+    free(e);
+    return ORC_OK;
+}
+
+/* Cholesky::det */
+double orc_dpotrf_det(size_t n, const double *l) {
+    double d = 1.0;
+    for (size_t i = 0; i < n; ++i) d = d * l[i * n + i];
+    return d * d;
+}
+
 /* Parity of a permutation via the reference's cycle-walking permute_by_swap
  * (permutation_matrix.rs:216-238, :479-509): +1 even, -1 odd.  Parity is a property of the
  * permutation, so any transposition decomposition gives the same sign. */

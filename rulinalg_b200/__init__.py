@@ -4,7 +4,7 @@ Matrix / MatrixSlice / Vector / PartialPivLu API.  All arithmetic runs in librla
 (hand-written CUDA; C ABI in include/rla_b200.h); there is no CPU fallback."""
 from .error import Error, ErrorKind, Panic
 from ._lib import RlaError, DeviceBuffer, lib, check, LIB_PATH, SYMBOLS
-from .matrix import Matrix, MatrixSlice, MatrixSliceMut, Vector, PermutationMatrix, PartialPivLu, LUP
+from .matrix import Matrix, MatrixSlice, MatrixSliceMut, Vector, PermutationMatrix, PartialPivLu, LUP, Cholesky
 
-__all__ = ["Matrix", "MatrixSlice", "MatrixSliceMut", "Vector", "PermutationMatrix", "PartialPivLu", "LUP",
+__all__ = ["Matrix", "MatrixSlice", "MatrixSliceMut", "Vector", "PermutationMatrix", "PartialPivLu", "LUP", "Cholesky",
            "Error", "ErrorKind", "Panic", "RlaError", "DeviceBuffer", "lib", "check", "LIB_PATH", "SYMBOLS"]

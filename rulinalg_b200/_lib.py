@@ -11,6 +11,7 @@ LIB_PATH = os.path.join(_HERE, "librla_b200.so")
 RLA_OK = 0
 RLA_ERR_SINGULAR = 1
 RLA_ERR_INVALID = 2
+RLA_ERR_NOT_POSITIVE = 3
 RLA_ERR_CUDA = -1
 RLA_ERR_NOMEM = -2
 RLA_ERR_NO_DEVICE = -3
@@ -20,6 +21,8 @@ SYMBOLS = [
     "rla_dgemm", "rla_sgemm", "rla_dgetrf", "rla_sgetrf", "rla_dgetrs", "rla_sgetrs",
     "rla_dgemv", "rla_sgemv", "rla_dgemv_dev", "rla_sgemv_dev", "rla_dtrsv", "rla_strsv", "rla_dgetri", "rla_sgetri", "rla_dgetri_dev", "rla_sgetri_dev",
     "rla_dgetrf_keep", "rla_dlu_solve", "rla_lu_free",
+    "rla_dpotrf", "rla_spotrf", "rla_dpotrs", "rla_spotrs", "rla_dpotri", "rla_spotri",
+    "rla_potrf_workspace_bytes", "rla_dpotrf_dev", "rla_spotrf_dev",
     "rla_init", "rla_device_count", "rla_dev_alloc", "rla_dev_free", "rla_host_alloc_pinned",
     "rla_host_free_pinned", "rla_memcpy_h2d", "rla_memcpy_d2h", "rla_stream_sync",
     "rla_dgemm_dev", "rla_sgemm_dev", "rla_dgetrf_dev", "rla_sgetrf_dev", "rla_dgetrs_dev", "rla_sgetrs_dev",
@@ -65,6 +68,14 @@ def lib():
         getattr(l, f).argtypes = [sz, P, P, P]
     for f in ("rla_dgetri_dev", "rla_sgetri_dev"):
         getattr(l, f).argtypes = [sz, P, sz, P, P, sz, P, P]
+    for f in ("rla_dpotrf", "rla_spotrf"):
+        getattr(l, f).argtypes = [sz, P]
+    for f in ("rla_dpotrs", "rla_spotrs", "rla_dpotri", "rla_spotri"):
+        getattr(l, f).argtypes = [sz, P, P]
+    l.rla_potrf_workspace_bytes.argtypes = [sz, sz]
+    l.rla_potrf_workspace_bytes.restype = sz
+    for f in ("rla_dpotrf_dev", "rla_spotrf_dev"):
+        getattr(l, f).argtypes = [sz, P, sz, P, P, P]
     l.rla_dgetrf_keep.argtypes = [sz, P, P, C.POINTER(P)]
     l.rla_dlu_solve.argtypes = [P, P]
     l.rla_lu_free.argtypes = [P]
@@ -104,8 +115,8 @@ def lib():
 
 
 def check(status: int) -> int:
-    """Raise on environment errors; return numerical statuses (0 / RLA_ERR_SINGULAR) to the caller."""
-    if status in (RLA_OK, RLA_ERR_SINGULAR):
+    """Raise on environment errors; return numerical statuses (0 / RLA_ERR_SINGULAR / RLA_ERR_NOT_POSITIVE) to the caller."""
+    if status in (RLA_OK, RLA_ERR_SINGULAR, RLA_ERR_NOT_POSITIVE):
         return status
     l = lib()
     msg = l.rla_strerror(status).decode()

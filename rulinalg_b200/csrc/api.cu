@@ -64,7 +64,7 @@ struct Context {
     cudaStream_t stream2 = nullptr;      // second compute stream (column strips of the host GEMM pipeline)
     cudaStream_t copy_in = nullptr;      // H2D
     cudaStream_t copy_out = nullptr;     // D2H
-    Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync, dTrsv;
+    Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync, dTrsv, dChol;
     Buffer hSmall;                       // pinned scalars (info, perm)
     LuWorkspace lu_ws;
     std::vector<cudaEvent_t> events;
@@ -413,6 +413,85 @@ int trsv_host(int lower, size_t n, const T *a, ptrdiff_t rs, T *x) {
     return RLA_OK;
 }
 
+// ---- Cholesky --------------------------------------------------------------------------------
+inline int potrf_status(int32_t info) { return info == 0 ? RLA_OK : (info > 0 ? RLA_ERR_SINGULAR : RLA_ERR_NOT_POSITIVE); }
+
+template <typename T>
+int potrf_host(size_t n, T *a) {
+    if (n == 0) return RLA_OK;
+    if (!a) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dChol.ensure(potrf_workspace_elems(n) * sizeof(T)));
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    T *dA = static_cast<T *>(cx.dA.p);
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p), *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    RLA_TRY(upload_matrix(dA, ld, a, n, n, n, cx.stream));
+    RLA_TRY(potrf_launch<T>(n, dA, ld, static_cast<T *>(cx.dChol.p), dInfo, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*hInfo != 0) return potrf_status(*hInfo);
+    RLA_TRY(download_matrix(a, n, dA, ld, n, n, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
+template <typename T>
+int potrs_host(size_t n, const T *l, T *b) {
+    if (n == 0) return RLA_OK;
+    if (!l || !b) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dC.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dVec.ensure(n * sizeof(T)));
+    RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(T)));
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.dSync.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    T *dA = static_cast<T *>(cx.dA.p), *dX = static_cast<T *>(cx.dVec.p);
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p), *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    RLA_TRY(upload_matrix(dA, ld, l, n, n, n, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(dX, b, n * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(potrs_launch<T>(n, dA, ld, dX, static_cast<T *>(cx.dC.p), static_cast<T *>(cx.dTrsv.p), dInfo, dInfo + 4,
+                            static_cast<int32_t *>(cx.dSync.p), cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*hInfo != 0) return RLA_ERR_SINGULAR;
+    RLA_CUDA(cudaMemcpyAsync(b, dX, n * sizeof(T), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
+template <typename T>
+int potri_host(size_t n, const T *l, T *inv) {
+    if (n == 0) return RLA_OK;
+    if (!l || !inv) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    Context &cx = tl_ctx;
+    const size_t ld = pad_ld(n, sizeof(T));
+    RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dB.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dC.ensure(n * ld * sizeof(T)));
+    RLA_TRY(cx.dPerm.ensure(n * sizeof(int64_t)));
+    RLA_TRY(cx.dInfo.ensure(64));
+    RLA_TRY(cx.hSmall.ensure(64));
+    T *dA = static_cast<T *>(cx.dA.p), *dM = static_cast<T *>(cx.dB.p), *dX = static_cast<T *>(cx.dC.p);
+    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p), *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+    RLA_TRY(upload_matrix(dA, ld, l, n, n, n, cx.stream));
+    RLA_TRY(potri_launch<T>(n, dA, ld, dX, ld, dM, static_cast<int64_t *>(cx.dPerm.p), dInfo, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*hInfo != 0) return RLA_ERR_SINGULAR;
+    RLA_TRY(download_matrix(inv, n, dX, ld, n, n, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    return RLA_OK;
+}
+
 template <typename T>
 int getri_host(size_t n, const T *lu, const size_t *perm, T *inv) {
     if (n == 0) return RLA_OK;
@@ -481,6 +560,22 @@ int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
                    void *stream) {
     RLA_TRY(ensure_ctx());
     return getri_launch<float>(n, lu, ld, d_perm, x, ldx, d_info, pick_stream(stream));
+}
+
+int rla_dpotrf(size_t n, double *a) { return potrf_host<double>(n, a); }
+int rla_spotrf(size_t n, float *a) { return potrf_host<float>(n, a); }
+int rla_dpotrs(size_t n, const double *l, double *b) { return potrs_host<double>(n, l, b); }
+int rla_spotrs(size_t n, const float *l, float *b) { return potrs_host<float>(n, l, b); }
+int rla_dpotri(size_t n, const double *l, double *inv) { return potri_host<double>(n, l, inv); }
+int rla_spotri(size_t n, const float *l, float *inv) { return potri_host<float>(n, l, inv); }
+size_t rla_potrf_workspace_bytes(size_t n, size_t elem_size) { return potrf_workspace_elems(n) * elem_size; }
+int rla_dpotrf_dev(size_t n, double *a, size_t ld, void *ws, int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return potrf_launch<double>(n, a, ld, static_cast<double *>(ws), d_info, pick_stream(stream));
+}
+int rla_spotrf_dev(size_t n, float *a, size_t ld, void *ws, int32_t *d_info, void *stream) {
+    RLA_TRY(ensure_ctx());
+    return potrf_launch<float>(n, a, ld, static_cast<float *>(ws), d_info, pick_stream(stream));
 }
 
 int rla_dgemv(size_t m, size_t n, const double *a, ptrdiff_t rs, const double *x, double *y) { return gemv_host<double>(m, n, a, rs, x, y); }
@@ -682,6 +777,7 @@ const char *rla_strerror(int status) {
         case RLA_OK: return "ok";
         case RLA_ERR_SINGULAR: return "matrix is singular to working precision (ErrorKind::DivByZero)";
         case RLA_ERR_INVALID: return "invalid argument";
+        case RLA_ERR_NOT_POSITIVE: return "diagonal entries of matrix are not all positive (ErrorKind::DecompFailure)";
         case RLA_ERR_CUDA: return "CUDA call failed (see rla_last_cuda_error)";
         case RLA_ERR_NOMEM: return "device or pinned-host allocation failed";
         case RLA_ERR_NO_DEVICE: return "no sm_100 (B200) device available; librla_b200 has no CPU fallback";

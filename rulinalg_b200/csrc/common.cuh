@@ -69,6 +69,15 @@ int getri_small_launch(int n, const T *lu, size_t ld, const int64_t *d_perm, T *
                        cudaStream_t st);
 template <typename T>
 int trsv_launch(bool lower, size_t n, const T *a, size_t ld, T *d_x, T *ws2, int32_t *d_info, int32_t *d_sync, cudaStream_t st);
+// Cholesky (cholesky.cu): in-place lower factor, solve, inverse.  info: 0 / j+1 (singular) / -(j+1) (negative diagonal).
+size_t potrf_workspace_elems(size_t n);
+template <typename T>
+int potrf_launch(size_t n, T *a, size_t ld, T *ws, int32_t *d_info, cudaStream_t st);
+template <typename T>
+int potrs_launch(size_t n, const T *l, size_t ld, T *d_b, T *lt, T *ws2, int32_t *d_info, int32_t *d_info2, int32_t *d_sync,
+                 cudaStream_t st);
+template <typename T>
+int potri_launch(size_t n, const T *l, size_t ld, T *x, size_t ldx, T *m, int64_t *d_perm, int32_t *d_info, cudaStream_t st);
 template <typename T>
 int gemv_launch(size_t m, size_t n, const T *a, size_t lda, const T *x, T *y, cudaStream_t st);
 size_t lu_plan_bytes();

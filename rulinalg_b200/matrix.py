@@ -404,3 +404,62 @@ class PartialPivLu:
         l = np.tril(a, -1) + np.eye(a.shape[0], dtype=a.dtype)
         u = np.triu(a)
         return LUP(Matrix._from_array(l), Matrix._from_array(u), self.p)
+
+
+class Cholesky:
+    """rulinalg::matrix::decomposition::Cholesky<T> over librla_b200 (cholesky.rs:94-245)."""
+
+    _SINGULAR_MSG = "Matrix is singular to working precision."
+    _NEGATIVE_MSG = "Diagonal entries of matrix are not all positive."
+    _L_SINGULAR_MSG = "Matrix L is singular to working precision."
+
+    def __init__(self, l: Matrix):
+        self.l = l                      # packed: lower triangle = L (strict upper triangle unspecified)
+
+    @staticmethod
+    def decompose(matrix: Matrix) -> "Cholesky":
+        n = matrix.cols()
+        if matrix.rows() != n:
+            raise Panic("Matrix must be square for Cholesky decomposition.")
+        a = matrix                                           # moved in, factorised in place (cholesky.rs:132)
+        pre = _dtype_pre(a._arr.dtype)
+        st = _lib.check(getattr(_lib.lib(), f"rla_{pre}potrf")(n, a.as_ptr()))
+        if st == _lib.RLA_ERR_SINGULAR:
+            raise Error(ErrorKind.DecompFailure, Cholesky._SINGULAR_MSG)
+        if st == _lib.RLA_ERR_NOT_POSITIVE:
+            raise Error(ErrorKind.DecompFailure, Cholesky._NEGATIVE_MSG)
+        return Cholesky(a)
+
+    def det(self):
+        # cholesky.rs:175-180: fold over the diagonal of L, squared
+        dt = self.l._arr.dtype.type
+        l_det = dt(1)
+        for v in np.diagonal(self.l._arr):
+            l_det = l_det * v
+        return l_det * l_det
+
+    def solve(self, b: Vector) -> Vector:
+        n = self.l.rows()
+        if b.size() != n:
+            raise Panic("RHS vector and coefficient matrix must be dimensionally compatible.")
+        x = np.array(b.data(), dtype=self.l._arr.dtype, copy=True)
+        pre = _dtype_pre(self.l._arr.dtype)
+        st = _lib.check(getattr(_lib.lib(), f"rla_{pre}potrs")(n, self.l.as_ptr(), x.ctypes.data))
+        if st == _lib.RLA_ERR_SINGULAR:
+            raise Error(ErrorKind.DivByZero, Cholesky._L_SINGULAR_MSG)
+        return Vector(x)
+
+    def inverse(self) -> Matrix:
+        # cholesky.rs:209-233 (n solves of unit vectors) as one blocked multi-RHS solve; n <= 64 keeps the exact order
+        n = self.l.rows()
+        dt = self.l._arr.dtype
+        inv = np.empty((n, n), dtype=dt)
+        pre = _dtype_pre(dt)
+        st = _lib.check(getattr(_lib.lib(), f"rla_{pre}potri")(n, self.l.as_ptr(), inv.ctypes.data))
+        if st == _lib.RLA_ERR_SINGULAR:
+            raise Error(ErrorKind.DivByZero, Cholesky._L_SINGULAR_MSG)
+        return Matrix._from_array(inv)
+
+    def unpack(self) -> Matrix:
+        # cholesky.rs:237-245: nullify_upper_triangular_part
+        return Matrix._from_array(np.tril(self.l._arr))

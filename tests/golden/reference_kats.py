@@ -98,3 +98,43 @@ FORWARD_SUBST = [
 ]
 # doc-test src/matrix/decomposition/lu.rs:218-230: identity(4) solve is the identity map
 SOLVE_IDENTITY = dict(n=4, b=[3.0, 4.0, 2.0, 1.0])
+
+# ----------------------------------------------------------------------------------------------
+# Cholesky: src/matrix/decomposition/cholesky.rs
+# ----------------------------------------------------------------------------------------------
+# doc-test :39-59 (comp = float)
+CHOL_DOC_3x3 = dict(a=[[1., 3., 1.], [3., 13., 11.], [1., 11., 21.]], l=[[1., 0., 0.], [3., 2., 0.], [1., 4., 2.]])
+# doc-test :65-79 (assert_vector_eq, exact)
+CHOL_DOC_SOLVE = dict(a=[[1., 3., 1.], [3., 13., 11.], [1., 11., 21.]],
+                      b1=[3., 2., 1.], b2=[-2., 1., 0.], y1=[23.25, -7.75, 3.0], y2=[-22.25, 7.75, -3.0])
+# tests :393-415 (comp = float)
+CHOL_UNPACK = [
+    dict(a=[[4.0]], l=[[2.0]]),
+    dict(a=[[9.0, -6.0], [-6.0, 20.0]], l=[[3.0, 0.0], [-2.0, 4.0]]),
+]
+# tests :418-442: decompose(x).is_err()
+CHOL_SINGULAR = [
+    [[0.0]],
+    [[0.0, 0.0], [0.0, 1.0]],
+    [[1.0, 0.0], [0.0, 0.0]],
+    [[1.0, 3.0, 5.0], [3.0, 9.0, 15.0], [5.0, 15.0, 65.0]],
+]
+# tests :452-466 (comp = float); empty -> 1.0 (:445-449)
+CHOL_DET = [
+    dict(a=[[1.0]], det=1.0),
+    dict(a=[[1.0, 3.0, 5.0], [3.0, 18.0, 33.0], [5.0, 33.0, 65.0]], det=36.0),
+]
+# tests :469-499 (comp = float)
+CHOL_SOLVE = [
+    dict(a=[[1.0]], b=[4.0], x=[4.0]),
+    dict(a=[[4.0, 6.0], [6.0, 25.0]], b=[2.0, 4.0], x=[0.40625, 0.0625]),
+]
+# tests :502-539 (comp = float)
+CHOL_INVERSE = [
+    dict(a=[[2.0]], inv=[[0.5]]),
+    dict(a=[[4.0, 6.0], [6.0, 25.0]], inv=[[0.390625, -0.09375], [-0.09375, 0.0625]]),
+    dict(a=[[9.0, 6.0, 3.0], [6.0, 20.0, 10.0], [3.0, 10.0, 14.0]],
+         inv=[[0.1388888888888889, -0.0416666666666667, 0.0],
+              [-0.0416666666666667, 0.0902777777777778, -0.0555555555555556],
+              [0.0, -0.0555555555555556, 0.1111111111111111]]),
+]

@@ -569,6 +569,128 @@ def test_lu_solve_device_resident_large_property(rla):
     assert err <= 1e-5, err
 
 
+# ------------------------------------------------------------------ Cholesky
+def spd(oracle, n, seed, dtype=np.float64):
+    """well-conditioned symmetric positive definite test matrix: M M^T / n + I from the seeded generator"""
+    m = oracle.fill_uniform((n, n), seed, np.float64, lo=-1.0, scale=2.0)
+    a = m @ m.T / n + np.eye(n)
+    a = (a + a.T) / 2
+    return np.ascontiguousarray(a.astype(dtype))
+
+
+def test_cholesky_kats_through_api(rla, oracle):
+    # cholesky.rs doc-tests :39-79 and tests :384-539 through the mirror API, with the reference's comparators
+    g = K.CHOL_DOC_3x3
+    oracle.assert_matrix_eq(rla.Cholesky.decompose(M(rla, g["a"])).unpack().to_numpy(), np.array(g["l"]), comp="float")
+    for g in K.CHOL_UNPACK:
+        oracle.assert_matrix_eq(rla.Cholesky.decompose(M(rla, g["a"])).unpack().to_numpy(), np.array(g["l"]), comp="float")
+    e = rla.Cholesky.decompose(rla.Matrix.zeros(0, 0))
+    assert e.unpack().to_numpy().shape == (0, 0) and e.det() == 1.0 and e.solve(rla.Vector([])).size() == 0
+    assert e.inverse().to_numpy().shape == (0, 0)
+    for n in (1, 2, 7, 30):                                  # quickcheck property :541-557
+        oracle.assert_matrix_eq(rla.Cholesky.decompose(M(rla, np.eye(n))).unpack().to_numpy(), np.eye(n), comp="float")
+    for g in K.CHOL_DET:
+        oracle.assert_matrix_eq(np.array([rla.Cholesky.decompose(M(rla, g["a"])).det()]), np.array([g["det"]]), comp="float")
+    for g in K.CHOL_SOLVE:
+        x = rla.Cholesky.decompose(M(rla, g["a"])).solve(rla.Vector(g["b"])).data()
+        oracle.assert_matrix_eq(x, np.array(g["x"]), comp="float")
+    g = K.CHOL_DOC_SOLVE
+    c = rla.Cholesky.decompose(M(rla, g["a"]))
+    oracle.assert_matrix_eq(c.solve(rla.Vector(g["b1"])).data(), np.array(g["y1"]), comp="exact")
+    oracle.assert_matrix_eq(c.solve(rla.Vector(g["b2"])).data(), np.array(g["y2"]), comp="exact")
+    for g in K.CHOL_INVERSE:
+        oracle.assert_matrix_eq(rla.Cholesky.decompose(M(rla, g["a"])).inverse().to_numpy(), np.array(g["inv"]), comp="float")
+
+
+def test_cholesky_errors_and_panics(rla):
+    for bad in K.CHOL_SINGULAR:                              # cholesky.rs:418-442
+        with pytest.raises(rla.Error) as ei:
+            rla.Cholesky.decompose(M(rla, bad))
+        assert ei.value.kind() == rla.ErrorKind.DecompFailure and "singular" in str(ei.value)
+    with pytest.raises(rla.Error) as ei:                     # negative diagonal (:155-158)
+        rla.Cholesky.decompose(M(rla, [[1.0, 0.0], [0.0, -4.0]]))
+    assert ei.value.kind() == rla.ErrorKind.DecompFailure and "not all positive" in str(ei.value)
+    with pytest.raises(rla.Panic):                           # :117-118, :377-381
+        rla.Cholesky.decompose(rla.Matrix.ones(2, 3))
+    with pytest.raises(rla.Panic):
+        rla.Cholesky.decompose(M(rla, np.eye(3))).solve(rla.Vector([1.0, 2.0]))
+    # a failure deep inside a blocked factorisation (column 300 of 400) is reported, not ignored
+    a = np.eye(400)
+    a[300, 300] = -1.0
+    with pytest.raises(rla.Error) as ei:
+        rla.Cholesky.decompose(M(rla, a))
+    assert "not all positive" in str(ei.value)
+    a[300, 300] = 0.0
+    with pytest.raises(rla.Error) as ei:
+        rla.Cholesky.decompose(M(rla, a))
+    assert "singular" in str(ei.value)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 9, 17, 33, 63, 64])
+def test_cholesky_bit_exact_within_one_block(rla, oracle, dtype, n):
+    # n <= 64: the diagonal-block kernel follows cholesky.rs:134-165 operation by operation (utils::dot's 8 partial sums)
+    a = spd(oracle, n, 100 + n, dtype)
+    a_upper_garbage = a.copy()
+    a_upper_garbage[np.triu_indices(n, 1)] = 12345.0          # only the lower triangle may be read
+    ref = oracle.cholesky_decompose(a)
+    c = rla.Cholesky.decompose(M(rla, a_upper_garbage, dtype))
+    oracle.assert_matrix_eq(c.unpack().to_numpy(), np.tril(ref), comp="exact")
+    b = oracle.fill_uniform((n,), 4000, dtype)
+    oracle.assert_matrix_eq(c.solve(rla.Vector(b)).data(), oracle.cholesky_solve(ref, b), comp="exact")
+    if dtype == np.float64:
+        oracle.assert_matrix_eq(c.inverse().to_numpy(), oracle.cholesky_inverse(ref), comp="exact")
+        assert c.det() == oracle.cholesky_det(ref)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [65, 200, 257, 300, 777, 1030])
+def test_cholesky_blocked_vs_oracle(rla, oracle, dtype, n):
+    # beyond one block the trailing updates run on the GEMM kernels (different summation order): gates are the
+    # reconstruction error (backward stability: |L L^T - A| <= c n u max|A|) and closeness to the oracle's factor
+    a = spd(oracle, n, 300 + n, dtype)
+    u = U(dtype)
+    ref = np.tril(oracle.cholesky_decompose(a)).astype(np.float64)
+    c = rla.Cholesky.decompose(M(rla, a, dtype))
+    l = c.unpack().to_numpy().astype(np.float64)
+    assert np.all(np.triu(l, 1) == 0)
+    recon = np.abs(l @ l.T - a.astype(np.float64)).max()
+    assert recon <= 8 * n * u * np.abs(a).max(), recon
+    assert np.abs(l - ref).max() <= 64 * n * u * np.abs(ref).max()
+    b = oracle.fill_uniform((n,), 4000, dtype)
+    x = c.solve(rla.Vector(b)).data().astype(np.float64)
+    xr = np.linalg.solve(a.astype(np.float64), b.astype(np.float64))
+    kappa = np.linalg.cond(a.astype(np.float64))
+    assert np.abs(x - xr).max() <= 64 * n * u * kappa * np.abs(xr).max()
+    if n <= 300:
+        inv = c.inverse().to_numpy().astype(np.float64)
+        assert np.abs(inv @ a.astype(np.float64) - np.eye(n)).max() <= 64 * n * u * kappa
+
+
+def test_cholesky_device_resident_large_property(rla):
+    # n = 8192 on the device: L L^T reproduces A on sampled rows, L is lower triangular with a positive diagonal
+    import torch
+    n = 8192
+    l = rla.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    g = torch.Generator(device="cuda").manual_seed(7)
+    m = torch.rand(n, n, dtype=torch.float64, device="cuda", generator=g) * 2 - 1
+    a0 = m @ m.T / n + torch.eye(n, dtype=torch.float64, device="cuda")     # checker-side product (torch)
+    a0 = (a0 + a0.T) / 2
+    a = a0.clone()
+    ws = torch.empty(int(l.rla_potrf_workspace_bytes(n, 8)), dtype=torch.uint8, device="cuda")
+    info = torch.ones(1, dtype=torch.int32, device="cuda")
+    assert l.rla_dpotrf_dev(n, a.data_ptr(), n, ws.data_ptr(), info.data_ptr(), s) == 0
+    torch.cuda.synchronize()
+    assert int(info.item()) == 0
+    lo = torch.tril(a)
+    assert float(torch.diagonal(lo).min().item()) > 0
+    rows = torch.tensor([0, 1, 63, 64, 255, 256, 1000, 4095, 4096, 8191], device="cuda")
+    recon = lo[rows] @ lo.T
+    err = float((recon - a0[rows]).abs().max().item())
+    assert err <= 8 * n * 2.0 ** -53 * float(a0.abs().max().item()), err
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_matrix_vector_product(rla, oracle, dtype):
     # &Matrix * &Vector (impl_ops.rs:298-314): row-wise utils::dot in the reference

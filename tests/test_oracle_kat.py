@@ -235,3 +235,64 @@ def test_comparators(oracle):
         oracle.assert_matrix_eq(np.zeros((2, 3)), np.zeros((3, 2)), comp="exact")   # dimension mismatch
     info = oracle.assert_matrix_eq(A([1.0, 2.0]), A([np.nextafter(1.0, 2), 2.0]), comp="ulp", tol=1)
     assert info["max_ulp"] == 1
+
+
+# ------------------------------------------------------------------ Cholesky KATs
+def test_cholesky_unpack_kats(oracle):
+    # cholesky.rs:39-59 (doc), :384-415
+    g = K.CHOL_DOC_3x3
+    oracle.assert_matrix_eq(oracle.cholesky_unpack(oracle.cholesky_decompose(A(g["a"]))), A(g["l"]), comp="float")
+    for g in K.CHOL_UNPACK:
+        oracle.assert_matrix_eq(oracle.cholesky_unpack(oracle.cholesky_decompose(A(g["a"]))), A(g["l"]), comp="float")
+    e = oracle.cholesky_unpack(oracle.cholesky_decompose(np.zeros((0, 0))))
+    assert e.shape == (0, 0)
+    # quickcheck property :541-557: cholesky(I) = I
+    for n in (1, 2, 7, 30):
+        oracle.assert_matrix_eq(oracle.cholesky_unpack(oracle.cholesky_decompose(np.eye(n))), np.eye(n), comp="float")
+
+
+def test_cholesky_only_lower_triangle_is_touched(oracle):
+    # decompose ignores the strict upper triangle (cholesky.rs:126-131): garbage there changes nothing below
+    a = A(K.CHOL_DOC_3x3["a"])
+    b = a.copy()
+    b[np.triu_indices(3, 1)] = 1e300
+    la, lb = oracle.cholesky_decompose(a), oracle.cholesky_decompose(b)
+    assert np.array_equal(np.tril(la), np.tril(lb))
+    assert np.array_equal(lb[np.triu_indices(3, 1)], b[np.triu_indices(3, 1)])
+
+
+def test_cholesky_failures(oracle):
+    # cholesky.rs:418-442 and the two messages :151-158
+    for bad in K.CHOL_SINGULAR:
+        with pytest.raises(oracle.DecompFailure, match="singular to working precision"):
+            oracle.cholesky_decompose(A(bad))
+    with pytest.raises(oracle.DecompFailure, match="not all positive"):
+        oracle.cholesky_decompose(A([[1.0, 0.0], [0.0, -4.0]]))
+    with pytest.raises(AssertionError):
+        oracle.cholesky_decompose(np.ones((2, 3)))
+
+
+def test_cholesky_det_solve_inverse_kats(oracle):
+    # cholesky.rs:445-466 (det), :469-499 (solve), :502-539 (inverse), doc :65-79
+    assert oracle.cholesky_det(oracle.cholesky_decompose(np.zeros((0, 0)))) == 1.0
+    for g in K.CHOL_DET:
+        oracle.assert_matrix_eq(np.array([oracle.cholesky_det(oracle.cholesky_decompose(A(g["a"])))]), np.array([g["det"]]), comp="float")
+    for g in K.CHOL_SOLVE:
+        oracle.assert_matrix_eq(oracle.cholesky_solve(oracle.cholesky_decompose(A(g["a"])), A(g["b"])), A(g["x"]), comp="float")
+    g = K.CHOL_DOC_SOLVE
+    l = oracle.cholesky_decompose(A(g["a"]))
+    oracle.assert_matrix_eq(oracle.cholesky_solve(l, A(g["b1"])), A(g["y1"]), comp="exact")
+    oracle.assert_matrix_eq(oracle.cholesky_solve(l, A(g["b2"])), A(g["y2"]), comp="exact")
+    for g in K.CHOL_INVERSE:
+        oracle.assert_matrix_eq(oracle.cholesky_inverse(oracle.cholesky_decompose(A(g["a"]))), A(g["inv"]), comp="float")
+    assert oracle.cholesky_solve(oracle.cholesky_decompose(np.zeros((0, 0))), np.zeros(0)).size == 0
+
+
+def test_transpose_back_substitution(oracle):
+    # cholesky.rs:329-365: L^T x = b
+    l = A([[2.0, 0.0, 0.0], [1.0, 3.0, 0.0], [4.0, 5.0, 6.0]])
+    x = A([1.0, -2.0, 0.5])
+    b = l.T @ x
+    oracle.assert_matrix_eq(oracle.transpose_back_substitution(l, b), x, comp="float")
+    with pytest.raises(oracle.DivByZero):
+        oracle.transpose_back_substitution(A([[1.0, 0.0], [1.0, 0.0]]), A([1.0, 1.0]))
