@@ -412,6 +412,27 @@ def extras(rla, l, torch, dev, sptr):
         out[f"dgetrs_{n}"] = {"ms": ms, "gbs": 8.0 * n * n / ms * 1e-6}
         del a0, a
         torch.cuda.empty_cache()
+    # Cholesky: flops = n^3 / 3; SPD input = G G^T / k + 4 I built with torch (checker side, untimed)
+    for n in (4096, 16384):
+        g = torch.rand(n, 2048, dtype=torch.float64, device=dev)
+        a0 = g @ g.T / 2048 + torch.eye(n, dtype=torch.float64, device=dev) * 4
+        del g
+        a = torch.empty_like(a0)
+        ws = torch.empty(int(l.rla_potrf_workspace_bytes(n, 8)), dtype=torch.uint8, device=dev)
+        info = torch.zeros(1, dtype=torch.int32, device=dev)
+        best = 1e30
+        for _ in range(3):
+            a.copy_(a0)
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            rla.check(l.rla_dpotrf_dev(n, a.data_ptr(), n, ws.data_ptr(), info.data_ptr(), sptr))
+            e1.record(stream); e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        tf = n ** 3 / 3.0 / best * 1e-9
+        out[f"dpotrf_{n}"] = {"ms": best, "tflops": tf, "frac_of_peak": tf / FP64_DMMA_PEAK_TFLOPS, "info": int(info.item())}
+        del a0, a, ws
+        torch.cuda.empty_cache()
     return out
 
 

@@ -56,6 +56,33 @@ def main():
                 print(json.dumps(rec), flush=True)
                 out.append(rec)
                 del a, b, c
+    if "chol" in which:
+        # Cholesky: flops n^3/3
+        for dt, fn, name, es in ((torch.float64, l.rla_dpotrf_dev, "dpotrf", 8), (torch.float32, l.rla_spotrf_dev, "spotrf", 4)):
+            for n in (1024, 4096, 8192, 16384, 32768):
+                if name == "spotrf" and n > 8192:
+                    continue
+                m = torch.rand(n, min(n, 2048), dtype=dt, device="cuda")
+                a0 = m @ m.T / m.shape[1] + torch.eye(n, dtype=dt, device="cuda") * 4     # SPD, checker-side product (torch)
+                del m
+                a = torch.empty_like(a0)
+                ws = torch.empty(int(l.rla_potrf_workspace_bytes(n, es)), dtype=torch.uint8, device="cuda")
+                info = torch.zeros(1, dtype=torch.int32, device="cuda")
+
+                def run():
+                    a.copy_(a0)
+                    rla.check(fn(n, a.data_ptr(), n, ws.data_ptr(), info.data_ptr(), s))
+
+                def copy_only():
+                    a.copy_(a0)
+
+                reps = 2 if n >= 16384 else 5
+                best, med = timed(run, reps, warm=1)
+                cbest, _ = timed(copy_only, reps, warm=1)
+                ms = best - cbest
+                print(json.dumps(dict(op=name, n=n, ms=ms, tflops=n ** 3 / 3 / ms * 1e-9, info=int(info.item()))), flush=True)
+                del a0, a, ws
+                torch.cuda.empty_cache()
     if "gemv" in which:
         for n in (4096, 16384, 32768):
             a = torch.rand(n, n, dtype=torch.float64, device="cuda"); x = torch.rand(n, dtype=torch.float64, device="cuda"); y = torch.empty(n, dtype=torch.float64, device="cuda")
