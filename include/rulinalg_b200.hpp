@@ -38,7 +38,7 @@ struct RlaFailure : std::runtime_error {
 
 namespace detail {
 inline int check(int st) {
-    if (st == RLA_OK || st == RLA_ERR_SINGULAR) return st;
+    if (st == RLA_OK || st == RLA_ERR_SINGULAR || st == RLA_ERR_NOT_POSITIVE) return st;
     throw RlaFailure(st);
 }
 template <typename T> struct Abi;
@@ -48,6 +48,9 @@ template <> struct Abi<double> {
     }
     static int getrf(size_t n, double *lu, size_t *p) { return rla_dgetrf(n, lu, p); }
     static int getrs(size_t n, const double *lu, const size_t *p, double *b) { return rla_dgetrs(n, lu, p, b); }
+    static int potrf(size_t n, double *a) { return rla_dpotrf(n, a); }
+    static int potrs(size_t n, const double *l, double *b) { return rla_dpotrs(n, l, b); }
+    static int potri(size_t n, const double *l, double *inv) { return rla_dpotri(n, l, inv); }
 };
 template <> struct Abi<float> {
     static int gemm(size_t m, size_t k, size_t n, const float *a, ptrdiff_t rsa, const float *b, ptrdiff_t rsb, float *c) {
@@ -55,6 +58,9 @@ template <> struct Abi<float> {
     }
     static int getrf(size_t n, float *lu, size_t *p) { return rla_sgetrf(n, lu, p); }
     static int getrs(size_t n, const float *lu, const size_t *p, float *b) { return rla_sgetrs(n, lu, p, b); }
+    static int potrf(size_t n, float *a) { return rla_spotrf(n, a); }
+    static int potrs(size_t n, const float *l, float *b) { return rla_spotrs(n, l, b); }
+    static int potri(size_t n, const float *l, float *inv) { return rla_spotri(n, l, inv); }
 };
 }  // namespace detail
 
@@ -207,6 +213,54 @@ class PartialPivLu {
   private:
     Matrix<T> lu_;
     PermutationMatrix p_;
+};
+
+// Cholesky<T> (src/matrix/decomposition/cholesky.rs:94-245)
+template <typename T>
+class Cholesky {
+  public:
+    // :116-170: consumes the matrix, factorises its lower triangle in place
+    static Cholesky decompose(Matrix<T> matrix) {
+        const size_t n = matrix.cols();
+        if (matrix.rows() != n) throw Panic("Matrix must be square for Cholesky decomposition.");
+        const int st = detail::check(detail::Abi<T>::potrf(n, matrix.as_mut_ptr()));
+        if (st == RLA_ERR_SINGULAR) throw Error(ErrorKind::DecompFailure, "Matrix is singular to working precision.");
+        if (st == RLA_ERR_NOT_POSITIVE) throw Error(ErrorKind::DecompFailure, "Diagonal entries of matrix are not all positive.");
+        Cholesky out;
+        out.l_ = std::move(matrix);
+        return out;
+    }
+    // :175-180
+    T det() const {
+        T l_det = T(1);
+        for (size_t i = 0; i < l_.rows(); ++i) l_det = l_det * l_(i, i);
+        return l_det * l_det;
+    }
+    // :194-203
+    Vector<T> solve(Vector<T> b) const {
+        if (b.size() != l_.rows()) throw Panic("RHS vector and coefficient matrix must be dimensionally compatible.");
+        if (detail::check(detail::Abi<T>::potrs(l_.rows(), l_.as_ptr(), b.mut_data().data())) == RLA_ERR_SINGULAR)
+            throw Error(ErrorKind::DivByZero, "Matrix L is singular to working precision.");
+        return b;
+    }
+    // :209-233
+    Matrix<T> inverse() const {
+        const size_t n = l_.rows();
+        Matrix<T> inv = Matrix<T>::zeros(n, n);
+        if (detail::check(detail::Abi<T>::potri(n, l_.as_ptr(), inv.as_mut_ptr())) == RLA_ERR_SINGULAR)
+            throw Error(ErrorKind::DivByZero, "Matrix L is singular to working precision.");
+        return inv;
+    }
+    // Decomposition::unpack (:237-245): L with the strict upper triangle zeroed
+    Matrix<T> unpack() const {
+        Matrix<T> l = l_;
+        T *p = l.as_mut_ptr();
+        for (size_t i = 0; i < l.rows(); ++i)
+            for (size_t j = i + 1; j < l.cols(); ++j) p[i * l.cols() + j] = T(0);
+        return l;
+    }
+  private:
+    Matrix<T> l_;
 };
 
 template <typename T>

@@ -6,6 +6,7 @@ use error::{Error, ErrorKind};
 
 pub const RLA_OK: i32 = 0;
 pub const RLA_ERR_SINGULAR: i32 = 1;
+pub const RLA_ERR_NOT_POSITIVE: i32 = 3;
 
 #[repr(C)]
 pub struct rla_lu_handle {
@@ -30,7 +31,30 @@ extern "C" {
     pub fn rla_dgetrf_keep(n: usize, lu: *mut f64, perm: *mut usize, out: *mut *mut rla_lu_handle) -> i32;
     pub fn rla_dlu_solve(h: *const rla_lu_handle, b: *mut f64) -> i32;
     pub fn rla_lu_free(h: *mut rla_lu_handle);
+    /// SURVEY 8f "next" rows: inverse, triangular solves, matrix-vector product, Cholesky (cholesky.rs:116-233).
+    pub fn rla_dgetri(n: usize, lu: *const f64, perm: *const usize, inv: *mut f64) -> i32;
+    pub fn rla_sgetri(n: usize, lu: *const f32, perm: *const usize, inv: *mut f32) -> i32;
+    pub fn rla_dtrsv(lower: i32, n: usize, a: *const f64, rs: isize, x: *mut f64) -> i32;
+    pub fn rla_strsv(lower: i32, n: usize, a: *const f32, rs: isize, x: *mut f32) -> i32;
+    pub fn rla_dgemv(m: usize, n: usize, a: *const f64, rs: isize, x: *const f64, y: *mut f64) -> i32;
+    pub fn rla_sgemv(m: usize, n: usize, a: *const f32, rs: isize, x: *const f32, y: *mut f32) -> i32;
+    pub fn rla_dpotrf(n: usize, a: *mut f64) -> i32;
+    pub fn rla_spotrf(n: usize, a: *mut f32) -> i32;
+    pub fn rla_dpotrs(n: usize, l: *const f64, b: *mut f64) -> i32;
+    pub fn rla_spotrs(n: usize, l: *const f32, b: *mut f32) -> i32;
+    pub fn rla_dpotri(n: usize, l: *const f64, inv: *mut f64) -> i32;
+    pub fn rla_spotri(n: usize, l: *const f32, inv: *mut f32) -> i32;
     pub fn rla_strerror(status: i32) -> *const ::std::os::raw::c_char;
+}
+
+/// Cholesky::decompose statuses (cholesky.rs:151-158): both are ErrorKind::DecompFailure.
+pub fn check_potrf(status: i32) -> Result<(), Error> {
+    match status {
+        RLA_OK => Ok(()),
+        RLA_ERR_SINGULAR => Err(Error::new(ErrorKind::DecompFailure, "Matrix is singular to working precision.")),
+        RLA_ERR_NOT_POSITIVE => Err(Error::new(ErrorKind::DecompFailure, "Diagonal entries of matrix are not all positive.")),
+        s => check(s, ""),
+    }
 }
 
 /// Numerical statuses become `Err(Error)`, environment failures (no device, CUDA error) panic:

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 
 #include "rulinalg_b200.hpp"
 
@@ -42,6 +43,25 @@ int main() {
         try { PartialPivLu<double>::decompose(Matrix<double>(4, 4, {1, 2, 3, 4, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0})); }
         catch (const Error &er) { div0 = er.kind() == ErrorKind::DivByZero; }
         REQUIRE(div0);
+        // Cholesky KATs: cholesky.rs:39-59 (unpack), :65-79 (solve, exact), :418-442 (singular), :502-539 (inverse)
+        auto ch = Cholesky<double>::decompose(Matrix<double>(3, 3, {1, 3, 1, 3, 13, 11, 1, 11, 21}));
+        const double lwant[9] = {1, 0, 0, 3, 2, 0, 1, 4, 2};
+        Matrix<double> lch = ch.unpack();
+        for (int i = 0; i < 9; ++i) REQUIRE(lch.data()[i] == lwant[i]);
+        Vector<double> y1 = ch.solve(Vector<double>({3, 2, 1}));
+        REQUIRE(y1[0] == 23.25 && y1[1] == -7.75 && y1[2] == 3.0);
+        REQUIRE(ch.det() == 16.0);
+        Matrix<double> inv2 = Cholesky<double>::decompose(Matrix<double>(2, 2, {4, 6, 6, 25})).inverse();
+        const double iwant[4] = {0.390625, -0.09375, -0.09375, 0.0625};
+        for (int i = 0; i < 4; ++i) REQUIRE(std::fabs(inv2.data()[i] - iwant[i]) <= 4 * 2.2e-16);
+        bool decomp_fail = false;
+        try { Cholesky<double>::decompose(Matrix<double>(3, 3, {1, 3, 5, 3, 9, 15, 5, 15, 65})); }
+        catch (const Error &er) { decomp_fail = er.kind() == ErrorKind::DecompFailure; }
+        REQUIRE(decomp_fail);
+        bool negative = false;
+        try { Cholesky<double>::decompose(Matrix<double>(2, 2, {1, 0, 0, -4})); }
+        catch (const Error &er) { negative = er.kind() == ErrorKind::DecompFailure && std::string(er.what()).find("not all positive") != std::string::npos; }
+        REQUIRE(negative);
     } catch (const RlaFailure &f) {
         std::fprintf(stderr, "%s\n", f.what());
         return f.status == RLA_ERR_NO_DEVICE ? 77 : 2;
