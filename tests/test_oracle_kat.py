@@ -296,3 +296,21 @@ def test_transpose_back_substitution(oracle):
     oracle.assert_matrix_eq(oracle.transpose_back_substitution(l, b), x, comp="float")
     with pytest.raises(oracle.DivByZero):
         oracle.transpose_back_substitution(A([[1.0, 0.0], [1.0, 0.0]]), A([1.0, 1.0]))
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+@pytest.mark.parametrize("n", [1, 5, 33, 64, 100])
+def test_cholesky_oracle_properties(oracle, dtype, n):
+    # not a reference test: the restatement must also BE a Cholesky factorisation (L L^T = A, agreement with LAPACK's
+    # factor within rounding, solve residual), so that the GPU parity tests compare against something meaningful
+    m = oracle.fill_uniform((n, n), 900 + n, np.float64, lo=-1.0, scale=2.0)
+    a = (m @ m.T / n + np.eye(n)).astype(dtype)
+    a = np.ascontiguousarray((a + a.T) / 2)
+    u = 2.0 ** (-52 if dtype == np.float64 else -23)
+    l = oracle.cholesky_unpack(oracle.cholesky_decompose(a)).astype(np.float64)
+    assert np.abs(l @ l.T - a.astype(np.float64)).max() <= 8 * n * u * np.abs(a).max()
+    assert np.abs(l - np.linalg.cholesky(a.astype(np.float64))).max() <= 64 * n * u * np.abs(l).max()
+    b = oracle.fill_uniform((n,), 4000, dtype)
+    x = oracle.cholesky_solve(oracle.cholesky_decompose(a), b).astype(np.float64)
+    r = np.abs(a.astype(np.float64) @ x - b.astype(np.float64)).max()
+    assert r <= 64 * n * u * np.abs(a).max() * max(np.abs(x).max(), 1.0)
