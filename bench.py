@@ -6,14 +6,19 @@
 
 Metric (BASELINE.json): DGEMM GFLOP/s, with % of the measured FP64 tensor (DMMA) peak in `roofline`.
 Workload at N=1: f64 `&A * &B`, A, B 8192 x 8192 (the point of BASELINE configs[1]'s sweep that the
->= 80 %-of-peak target is quoted on).  A "step" is one full product.  At N>1 the product is sharded
-as row panels (weak scaling: every GPU owns 8192 rows of A and C, B is broadcast from rank 0 over
-NCCL in k chunks overlapped with the kernel; at N=8 this is a 65536 x 8192 x 8192 product).
+>= 80 %-of-peak target is quoted on).  A "step" is one full product.
+Workload at N>1: BASELINE configs[3] (C4) as SURVEY 8d states it -- the weak series m = 4096*N, k = n = 32768:
+every GPU owns 4096 rows of A and C, B (8 GiB) is broadcast from rank 0 over NCCL in 16 k chunks of 2048 rows
+overlapped with the DMMA kernel.  The strong 32768^3 point and C5 (LU n = 32768, 1D block-cyclic) are in `extras`.
+Every N>1 run verifies itself: Freivalds + sampled extended-precision entries per rank for the GEMM, sampled-row
+reconstruction P A = L U for the distributed LU (`parity_ok`).
 
   value  = whole-job GFLOP/s with operands resident in HBM (CUDA events, max over ranks)
-  e2e    = same metric through the reference-facing host call (rla_dgemm with pinned HOST buffers;
-           H2D of A and B and D2H of C inside the timed region)
-  extras = the other BASELINE configs measured the same way at N=1 (SGEMM, LU, solve, sweep points)
+  e2e    = same metric through the reference-facing host call: rla_dgemm with HOST buffers, H2D of A and B and
+           D2H of C inside the timed region; at N>1 rank 0 makes that one call after rla_set_devices(N)
+           (one host process driving N GPUs -- what a Rust caller gets), the other ranks idle
+  extras = the other BASELINE configs measured the same way (SGEMM, LU, solve, sweep points, host-API LU,
+           pageable-memory e2e, the reference's own bench shapes)
 """
 from __future__ import annotations
 
@@ -30,9 +35,30 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 N_SQUARE = 8192
-FP64_DMMA_PEAK_TFLOPS = 37.13     # measured on this pool by tools/peaks.cu (profiles/peaks_r01.jsonl)
-FP32_FFMA_PEAK_TFLOPS = 72.4      # idem
+N_WIDE = 32768                    # C4 / C5 width
+M_PER_GPU_WEAK = 4096             # C4 weak series: rows of A per GPU
+# fallbacks only: the peaks are measured in-run by rla_measure_peak (register-only DMMA / FFMA loops on every SM)
+FP64_DMMA_PEAK_TFLOPS = 37.13     # profiles/peaks_r01.jsonl
+FP32_FFMA_PEAK_TFLOPS = 72.4
 HBM_PEAK_GBS_FALLBACK = 6650.0
+
+
+def measured_peaks(l):
+    """(fp64 DMMA TFLOP/s, fp32 FFMA TFLOP/s, source) measured on the current device, constants if that fails"""
+    import ctypes as C
+    out = []
+    for kind, fb in ((0, FP64_DMMA_PEAK_TFLOPS), (1, FP32_FFMA_PEAK_TFLOPS)):
+        v = C.c_double(0.0)
+        st = l.rla_measure_peak(kind, C.byref(v))
+        out.append(v.value if st == 0 and v.value > 0 else fb)
+    return out[0], out[1], "measured in this run by rla_measure_peak (issue-bound DMMA.8x8x4 / FFMA register loops, 1024 threads x 148 SMs)"
+
+
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return HBM_PEAK_GBS_FALLBACK, "fallback (B200_PROFILING.md)"
 
 
 def parse():

@@ -136,6 +136,20 @@ RLA_API void rla_lu_free(rla_lu_handle *h);
  * ------------------------------------------------------------------------------------- */
 RLA_API int rla_init(int device);                 /* select device + create context; idempotent      */
 RLA_API int rla_device_count(void);
+/* One host process, N GPUs (north_star: "Large GEMMs are sharded as row panels across 2/4/8 GPUs ...
+ * large LU uses a 1D block-cyclic column layout").  After rla_set_devices(N) the host-pointer entry points rla_dgemm /
+ * rla_sgemm / rla_dgetrf -- the only calls the reference sites mat_mul.rs:33-43,57-67 and lu.rs:163-195 can reach --
+ * shard large problems over GPUs 0..N-1: GEMM as row panels of A and C with every column chunk of B uploaded once
+ * (chunks dealt round-robin over the N PCIe links) and fanned out over NVLink peer memory; LU as 256-column blocks
+ * dealt round-robin with the factored panel fanned out the same way.  Results are bit-identical to N = 1.  Small
+ * problems stay on one GPU.  N = 1 (default) restores single-GPU behaviour.  RLA_ERR_INVALID when N exceeds the
+ * visible devices or the GPUs lack peer access.  Process-wide; multi-GPU calls from several host threads serialise. */
+RLA_API int rla_set_devices(int n_gpus);
+RLA_API int rla_get_devices(void);
+/* Returns everything the library holds for the calling host thread (streams, events, device and pinned buffers, LU
+ * workspaces, staging rings) and the multi-GPU contexts.  Also runs when a host thread exits.  Later calls
+ * re-initialise lazily.  (SURVEY 8b "Ownership": device memory is owned by the library, freed at rla_shutdown.) */
+RLA_API int rla_shutdown(void);
 RLA_API int rla_dev_alloc(void **p, size_t bytes);
 RLA_API int rla_dev_free(void *p);
 RLA_API int rla_host_alloc_pinned(void **p, size_t bytes);
@@ -209,8 +223,14 @@ RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_
  * (see csrc/dgemm.cu).  "lu_gmax": cap on the panel kernel's row
  * CTAs.  "lu_cluster": 1 (default) = panels that fit one thread-block cluster use the DSMEM panel kernel, 0 = always
  * the grid-wide kernel.  "host_gemm_2d": 1 (default) = 2-D wavefront pipeline for large host-pointer products, 0 = row panels;
- * "host_gemm_s": strips per dimension of that pipeline, 0 (default) = auto.  "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
+ * "host_gemm_s": strips per dimension of that pipeline, 0 (default) = auto.  "host_stage": 1 (default) = pageable host
+ * operands of large calls travel through the library's pinned staging ring (host.cu), 0 = plain cudaMemcpyAsync on them.
+ * "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
 RLA_API int rla_set_tuning(const char *key, int value);
+
+/* Roofline denominators measured on the current device: issue-bound register loops on every SM.
+ * kind 0: FP64 tensor pipe (DMMA.8x8x4); kind 1: FP32 FMA pipe (FFMA).  ~30 ms. */
+RLA_API int rla_measure_peak(int kind, double *tflops);
 
 /* Diagnostics */
 RLA_API const char *rla_strerror(int status);

@@ -23,13 +23,13 @@ SYMBOLS = [
     "rla_dgetrf_keep", "rla_dlu_solve", "rla_lu_free",
     "rla_dpotrf", "rla_spotrf", "rla_dpotrs", "rla_spotrs", "rla_dpotri", "rla_spotri",
     "rla_potrf_workspace_bytes", "rla_dpotrf_dev", "rla_spotrf_dev",
-    "rla_init", "rla_device_count", "rla_dev_alloc", "rla_dev_free", "rla_host_alloc_pinned",
+    "rla_init", "rla_device_count", "rla_set_devices", "rla_get_devices", "rla_shutdown", "rla_dev_alloc", "rla_dev_free", "rla_host_alloc_pinned",
     "rla_host_free_pinned", "rla_memcpy_h2d", "rla_memcpy_d2h", "rla_stream_sync",
     "rla_dgemm_dev", "rla_sgemm_dev", "rla_dgetrf_dev", "rla_sgetrf_dev", "rla_dgetrs_dev", "rla_sgetrs_dev",
     "rla_fill_uniform_f64_dev", "rla_fill_uniform_f32_dev",
     "rla_lu_plan_bytes", "rla_debug_lu_trace", "rla_dlu_factor_block_dev", "rla_dlu_laswp_dev", "rla_dlu_update_dev",
     "rla_lu_rowid_init_dev", "rla_lu_rowid_apply_dev", "rla_lu_perm_from_rowid_dev",
-    "rla_set_tuning", "rla_strerror", "rla_last_cuda_error", "rla_version", "rla_launch_count", "rla_launch_count_reset",
+    "rla_measure_peak", "rla_set_tuning", "rla_strerror", "rla_last_cuda_error", "rla_version", "rla_launch_count", "rla_launch_count_reset",
 ]
 
 
@@ -81,6 +81,7 @@ def lib():
     l.rla_lu_free.argtypes = [P]
     l.rla_lu_free.restype = None
     l.rla_init.argtypes = [i32]
+    l.rla_set_devices.argtypes = [i32]
     l.rla_dev_alloc.argtypes = [C.POINTER(P), sz]
     l.rla_dev_free.argtypes = [P]
     l.rla_host_alloc_pinned.argtypes = [C.POINTER(P), sz]
@@ -104,6 +105,7 @@ def lib():
     l.rla_lu_rowid_init_dev.argtypes = [P, sz, P]
     l.rla_lu_rowid_apply_dev.argtypes = [P, P, P, P]
     l.rla_lu_perm_from_rowid_dev.argtypes = [P, P, sz, P, P]
+    l.rla_measure_peak.argtypes = [i32, C.POINTER(dbl)]
     l.rla_set_tuning.argtypes = [C.c_char_p, i32]
     l.rla_strerror.argtypes = [i32]
     l.rla_strerror.restype = C.c_char_p

@@ -7,10 +7,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
 #include <mutex>
 #include <vector>
 
-#include "common.cuh"
+#include "context.cuh"
 
 namespace rla {
 
@@ -18,99 +19,166 @@ extern int g_dgemm_cfg;   // dgemm.cu
 extern int g_lu_gmax, g_lu_dbg, g_lu_cluster;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 int g_host_gemm_s = 0;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline; 0 = auto (~512-row strips)
+int g_host_stage = 1;             // rla_set_tuning("host_stage", 0/1): pageable operands through the pinned staging ring (host.cu)
+
+namespace {
+thread_local cudaError_t tl_last_cuda = cudaSuccess;
+thread_local uint64_t tl_launches = 0;
+}  // namespace
+
+int Buffer::ensure(size_t bytes) {
+    if (bytes <= cap) return RLA_OK;
+    release();
+    // grow geometrically to avoid realloc churn on size sweeps
+    size_t want = bytes + bytes / 8;
+    cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        want = bytes;
+        e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
+    }
+    if (e != cudaSuccess) {
+        p = nullptr;
+        note_cuda_error(e);
+        cudaGetLastError();
+        return RLA_ERR_NOMEM;
+    }
+    cap = want;
+    return RLA_OK;
+}
+void Buffer::release() {
+    if (p) {
+        if (pinned_host) cudaFreeHost(p); else cudaFree(p);
+        (void)cudaGetLastError();
+    }
+    p = nullptr;
+    cap = 0;
+}
+
+int Context::init(int dev) {
+    if (ready && device == dev) return RLA_OK;
+    destroy();
+    RLA_CUDA(cudaSetDevice(dev));
+    device = dev;
+    RLA_CUDA(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+    RLA_CUDA(cudaStreamCreateWithFlags(&stream2, cudaStreamNonBlocking));
+    RLA_CUDA(cudaStreamCreateWithFlags(&copy_in, cudaStreamNonBlocking));
+    RLA_CUDA(cudaStreamCreateWithFlags(&copy_out, cudaStreamNonBlocking));
+    RLA_CUDA(cudaStreamCreateWithFlags(&p2p, cudaStreamNonBlocking));
+    ready = true;
+    return RLA_OK;
+}
+
+// Everything this context allocated goes back: streams, events, device and pinned buffers, the LU workspace and the
+// staging ring.  Runs at host-thread exit (thread_local destructor), from rla_shutdown, and is harmless when the CUDA
+// runtime is already unloading (every call then just fails).
+void Context::destroy() {
+    if (device < 0) return;
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { (void)cudaGetLastError(); cur = -1; }
+    if (cudaSetDevice(device) == cudaSuccess) {
+        for (cudaStream_t *s : {&stream, &stream2, &copy_in, &copy_out, &p2p}) {
+            if (*s) { cudaStreamSynchronize(*s); cudaStreamDestroy(*s); }
+            *s = nullptr;
+        }
+        stager.release();
+        for (cudaEvent_t e : events) cudaEventDestroy(e);
+        events.clear();
+        for (Buffer *b : {&dA, &dB, &dC, &dPerm, &dInfo, &dVec, &dVec2, &dSync, &dTrsv, &dChol, &dPanel[0], &dPanel[1], &dRowid, &hSmall})
+            b->release();
+        lu_workspace_release(lu_ws);
+    }
+    (void)cudaGetLastError();
+    if (cur >= 0) cudaSetDevice(cur);
+    (void)cudaGetLastError();
+    ready = false;
+    device = -1;
+}
+
+int Context::event(size_t i, cudaEvent_t *out) {
+    while (events.size() <= i) {
+        cudaEvent_t e;
+        RLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        events.push_back(e);
+    }
+    *out = events[i];
+    return RLA_OK;
+}
 
 namespace {
 
-thread_local cudaError_t tl_last_cuda = cudaSuccess;
-thread_local uint64_t tl_launches = 0;
-
-struct Buffer {
-    void *p = nullptr;
-    size_t cap = 0;
-    bool pinned_host = false;
-    int ensure(size_t bytes) {
-        if (bytes <= cap) return RLA_OK;
-        release();
-        // grow geometrically to avoid realloc churn on size sweeps
-        size_t want = bytes + bytes / 8;
-        cudaError_t e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            cudaGetLastError();
-            want = bytes;
-            e = pinned_host ? cudaMallocHost(&p, want) : cudaMalloc(&p, want);
-        }
-        if (e != cudaSuccess) {
-            p = nullptr;
-            note_cuda_error(e);
-            cudaGetLastError();
-            return RLA_ERR_NOMEM;
-        }
-        cap = want;
-        return RLA_OK;
-    }
-    void release() {
-        if (p) {
-            if (pinned_host) cudaFreeHost(p); else cudaFree(p);
-        }
-        p = nullptr;
-        cap = 0;
-    }
+// One context per (host thread, device): a thread that moves between devices (rla_init(d), or the caller's own
+// cudaSetDevice for the *_dev twins) gets separate streams, buffers and workspaces on each of them.
+struct ThreadContexts {
+    std::unique_ptr<Context> per_dev[RLA_MAX_DEVICES];
 };
-
-struct Context {
-    bool ready = false;
-    int device = -1;
-    cudaStream_t stream = nullptr;       // compute
-    cudaStream_t stream2 = nullptr;      // second compute stream (column strips of the host GEMM pipeline)
-    cudaStream_t copy_in = nullptr;      // H2D
-    cudaStream_t copy_out = nullptr;     // D2H
-    Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync, dTrsv, dChol;
-    Buffer hSmall;                       // pinned scalars (info, perm)
-    LuWorkspace lu_ws;
-    std::vector<cudaEvent_t> events;
-    Context() {
-        hSmall.pinned_host = true;
-    }
-};
-thread_local Context tl_ctx;
+thread_local ThreadContexts tl_ctxs;
 
 std::once_flag g_dev_once;
-int g_dev_status = RLA_ERR_NO_DEVICE;
 int g_dev_count = 0;
+bool g_dev_ok[RLA_MAX_DEVICES] = {};
 
 void probe_devices() {
     int cnt = 0;
     cudaError_t e = cudaGetDeviceCount(&cnt);
     if (e != cudaSuccess || cnt == 0) {
         cudaGetLastError();
-        g_dev_status = RLA_ERR_NO_DEVICE;
+        g_dev_count = 0;
         return;
     }
+    if (cnt > RLA_MAX_DEVICES) cnt = RLA_MAX_DEVICES;
+    for (int d = 0; d < cnt; ++d) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, d) != cudaSuccess) { cudaGetLastError(); major = 0; }
+        g_dev_ok[d] = (major == 10);       // kernels are sm_100a only; no fallback
+    }
     g_dev_count = cnt;
-    g_dev_status = RLA_OK;
 }
 
-int ensure_ctx(int device = -1) {
+}  // namespace
+
+int probe_device_count() {
     std::call_once(g_dev_once, probe_devices);
-    if (g_dev_status != RLA_OK) return g_dev_status;
-    Context &c = tl_ctx;
-    if (c.ready && (device < 0 || device == c.device)) return RLA_OK;
+    return g_dev_count;
+}
+
+bool device_usable(int d) { return d >= 0 && d < probe_device_count() && g_dev_ok[d]; }
+
+Context &thread_ctx() {
+    const int d = current_device();
+    if (!tl_ctxs.per_dev[d]) tl_ctxs.per_dev[d].reset(new Context());
+    return *tl_ctxs.per_dev[d];
+}
+
+// Binds the calling thread to `device` (or to its current CUDA device when device < 0) and makes sure the
+// (thread, device) context exists.  Every entry point starts here, so the device is always the one the context's
+// streams and buffers live on.
+int ensure_ctx(int device) {
+    if (probe_device_count() == 0) return RLA_ERR_NO_DEVICE;
     if (device < 0) {
         if (cudaGetDevice(&device) != cudaSuccess) { cudaGetLastError(); return RLA_ERR_NO_DEVICE; }
+    } else {
+        if (device >= g_dev_count) return RLA_ERR_NO_DEVICE;
+        RLA_CUDA(cudaSetDevice(device));
     }
-    if (device >= g_dev_count) return RLA_ERR_NO_DEVICE;
-    cudaDeviceProp prop;
-    RLA_CUDA(cudaGetDeviceProperties(&prop, device));
-    if (prop.major != 10) return RLA_ERR_NO_DEVICE;   // kernels are sm_100a only; no fallback
-    RLA_CUDA(cudaSetDevice(device));
-    if (!c.stream) RLA_CUDA(cudaStreamCreateWithFlags(&c.stream, cudaStreamNonBlocking));
-    if (!c.stream2) RLA_CUDA(cudaStreamCreateWithFlags(&c.stream2, cudaStreamNonBlocking));
-    if (!c.copy_in) RLA_CUDA(cudaStreamCreateWithFlags(&c.copy_in, cudaStreamNonBlocking));
-    if (!c.copy_out) RLA_CUDA(cudaStreamCreateWithFlags(&c.copy_out, cudaStreamNonBlocking));
-    c.device = device;
-    c.ready = true;
-    return RLA_OK;
+    if (device >= g_dev_count || !g_dev_ok[device]) return RLA_ERR_NO_DEVICE;
+    Context &c = thread_ctx();
+    if (c.ready) return RLA_OK;
+    return c.init(device);
 }
+
+template <>
+int gemm_dev<double>(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b,
+                     size_t ldb, double beta, double *c, size_t ldc, cudaStream_t st) {
+    return dgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+}
+template <>
+int gemm_dev<float>(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b,
+                    size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
+    return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+}
+
+namespace {
 
 cudaStream_t pick_stream(void *s) { return static_cast<cudaStream_t>(s); }   // NULL = CUDA legacy default stream
 
@@ -126,25 +194,6 @@ int download_matrix(T *dst, size_t rs, const T *src, size_t ld, size_t rows, siz
     if (rows == 0 || cols == 0) return RLA_OK;
     RLA_CUDA(cudaMemcpy2DAsync(dst, rs * sizeof(T), src, ld * sizeof(T), cols * sizeof(T), rows, cudaMemcpyDeviceToHost, st));
     return RLA_OK;
-}
-
-inline size_t pad_ld(size_t cols, size_t elem) {
-    const size_t q = 16 / elem;          // keep rows 16-byte aligned so the cp.async fast path applies
-    return (cols + q - 1) / q * q;
-}
-
-template <typename T>
-int gemm_dev(size_t m, size_t k, size_t n, T alpha, const T *a, size_t lda, const T *b, size_t ldb, T beta, T *c,
-             size_t ldc, cudaStream_t st);
-template <>
-int gemm_dev<double>(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b,
-                     size_t ldb, double beta, double *c, size_t ldc, cudaStream_t st) {
-    return dgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
-}
-template <>
-int gemm_dev<float>(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b,
-                    size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
-    return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
 // Host operand with arbitrary (possibly negative / non-unit) strides -> packed row-major copy.
@@ -164,7 +213,7 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
     if (m == 0 || n == 0) return RLA_OK;
     if ((k > 0 && (!a || !b)) || !c) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
 
     std::vector<T> pa, pb, pc;
     const T *ha = a, *hb = b;
@@ -180,11 +229,27 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         hrsc = n;
     }
 
+    // Pageable operands (what a Rust Vec<T> is) travel through the pinned staging ring; pinned ones are DMA'd in place.
+    Stager &stg = cx.stager;
+    const bool stage = g_host_stage != 0;
+    const bool pin_a = !stage || host_is_pinned(ha), pin_b = !stage || host_is_pinned(hb), pin_c = !stage || host_is_pinned(hc);
+    const double flops = 2.0 * double(m) * double(k) * double(n);
+    const int ndev = multi_device_count();
+    if (ndev > 1 && beta == T(0) && k > 0 && m >= size_t(256) * ndev && n >= 1024 && flops >= 4e11) {
+        // rla_set_devices(N): row panels of A and C over N GPUs, B chunks fanned out over NVLink (multi.cu)
+        RLA_TRY(gemm_host_multi<T>(m, k, n, alpha, ha, hrsa, hb, hrsb, hc, hrsc, stg));
+    } else {
     const size_t lda = pad_ld(k ? k : 1, sizeof(T)), ldb = pad_ld(n, sizeof(T)), ldc = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(m * lda * sizeof(T)));
     RLA_TRY(cx.dB.ensure((k ? k : 1) * ldb * sizeof(T)));
     RLA_TRY(cx.dC.ensure(m * ldc * sizeof(T)));
     T *dA = static_cast<T *>(cx.dA.p), *dB = static_cast<T *>(cx.dB.p), *dC = static_cast<T *>(cx.dC.p);
+    auto up = [&](T *dst, size_t ld, const T *src, size_t rs, size_t rows, size_t cols, bool pinned) -> int {
+        return stg.upload2d(dst, ld * sizeof(T), src, rs * sizeof(T), cols * sizeof(T), rows, pinned, cx.device, cx.copy_in);
+    };
+    auto down = [&](T *dst, size_t rs, const T *src, size_t ld, size_t rows, size_t cols) -> int {
+        return stg.download2d(dst, rs * sizeof(T), src, ld * sizeof(T), cols * sizeof(T), rows, pin_c, cx.device, cx.copy_out);
+    };
 
     const size_t bytes_per_row = (k + n) * sizeof(T);
     const bool big = m * bytes_per_row > (size_t(96) << 20);
@@ -211,8 +276,8 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
             const size_t r0 = st * pm, c0 = st * pn;
             const size_t rows = st < sm ? (r0 + pm <= m ? pm : m - r0) : 0;
             const size_t cols = st < sn ? (c0 + pn <= n ? pn : n - c0) : 0;
-            if (rows) RLA_TRY(upload_matrix(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, cx.copy_in));
-            if (cols) RLA_TRY(upload_matrix(dB + c0, ldb, hb + c0, hrsb, k, cols, cx.copy_in));
+            if (rows) RLA_TRY(up(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, pin_a));
+            if (cols) RLA_TRY(up(dB + c0, ldb, hb + c0, hrsb, k, cols, pin_b));
             cudaEvent_t ev_in = cx.events[3 * st], ev_row = cx.events[3 * st + 1], ev_col = cx.events[3 * st + 2];
             RLA_CUDA(cudaEventRecord(ev_in, cx.copy_in));
             // row strip: rows of panel st against every chunk uploaded so far (including this step's);
@@ -232,11 +297,11 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
             }
             if (rows) {
                 RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, ev_row, 0));
-                RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, ncols_avail, cx.copy_out));
+                RLA_TRY(down(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, ncols_avail));
             }
             if (cols && nrows_prev) {
                 RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, ev_col, 0));
-                RLA_TRY(download_matrix(hc + c0, hrsc, dC + c0, ldc, nrows_prev, cols, cx.copy_out));
+                RLA_TRY(down(hc + c0, hrsc, dC + c0, ldc, nrows_prev, cols));
             }
         }
     } else {
@@ -253,42 +318,49 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         RLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         cx.events.push_back(e);
     }
-    RLA_TRY(upload_matrix(dB, ldb, hb, hrsb, k, n, cx.copy_in));
+    RLA_TRY(up(dB, ldb, hb, hrsb, k, n, pin_b));
     for (size_t p = 0; p < npanels; ++p) {
         const size_t r0 = p * panel, rows = (r0 + panel <= m) ? panel : m - r0;
-        RLA_TRY(upload_matrix(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, cx.copy_in));
-        if (beta != T(0)) RLA_TRY(upload_matrix(dC + r0 * ldc, ldc, hc + r0 * hrsc, hrsc, rows, n, cx.copy_in));
+        RLA_TRY(up(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, pin_a));
+        if (beta != T(0)) RLA_TRY(up(dC + r0 * ldc, ldc, hc + r0 * hrsc, hrsc, rows, n, pin_c));
         RLA_CUDA(cudaEventRecord(cx.events[2 * p], cx.copy_in));
         RLA_CUDA(cudaStreamWaitEvent(cx.stream, cx.events[2 * p], 0));
         RLA_TRY(gemm_dev<T>(rows, k, n, alpha, dA + r0 * lda, lda, dB, ldb, beta, dC + r0 * ldc, ldc, cx.stream));
         RLA_CUDA(cudaEventRecord(cx.events[2 * p + 1], cx.stream));
         RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, cx.events[2 * p + 1], 0));
-        RLA_TRY(download_matrix(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, n, cx.copy_out));
+        RLA_TRY(down(hc + r0 * hrsc, hrsc, dC + r0 * ldc, ldc, rows, n));
     }
     }
     RLA_CUDA(cudaStreamSynchronize(cx.copy_out));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
     RLA_CUDA(cudaStreamSynchronize(cx.stream2));
+    RLA_TRY(stg.finish());           // pageable C: the last staged pieces are copied out by the drainer
+    }
     if (!c_direct)
         for (size_t i = 0; i < m; ++i)
             for (size_t j = 0; j < n; ++j) c[ptrdiff_t(i) * rsc + ptrdiff_t(j) * csc] = pc[i * n + j];
     return RLA_OK;
 }
 
+// PartialPivLu::decompose through host memory (lu.rs:163-195 consumes a Vec): upload, factor, and download every block
+// row as soon as it can no longer change (getrf_launch's rows_final hook), so the D2H of the factors runs under the
+// factorisation of the rest instead of after it.  Pageable memory travels through the staging ring.
 template <typename T>
 int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm, size_t *keep_ld) {
     if (n == 0) return RLA_OK;
     if (!lu || !perm) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
+    if (!keep_dev && multi_device_count() > 1 && n >= 8192)      // rla_set_devices(N): 1D block-cyclic over N GPUs (multi.cu)
+        return getrf_host_multi<T>(n, lu, perm, cx.stager);
     const size_t ld = pad_ld(n, sizeof(T));
     T *dA;
     int64_t *dP;
+    void *p1 = nullptr, *p2 = nullptr;
     if (keep_dev) {
-        void *p1 = nullptr, *p2 = nullptr;
         RLA_CUDA(cudaMalloc(&p1, n * ld * sizeof(T)));
-        cudaError_t e = cudaMalloc(&p2, n * sizeof(int64_t));
-        if (e != cudaSuccess) { cudaFree(p1); note_cuda_error(e); return RLA_ERR_NOMEM; }
+        const cudaError_t e = cudaMalloc(&p2, n * sizeof(int64_t));
+        if (e != cudaSuccess) { cudaFree(p1); (void)cudaGetLastError(); note_cuda_error(e); return RLA_ERR_NOMEM; }
         dA = static_cast<T *>(p1);
         dP = static_cast<int64_t *>(p2);
     } else {
@@ -297,35 +369,47 @@ int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm,
         dA = static_cast<T *>(cx.dA.p);
         dP = static_cast<int64_t *>(cx.dPerm.p);
     }
-    RLA_TRY(cx.dInfo.ensure(64));
-    RLA_TRY(cx.hSmall.ensure(64));
-    int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p);
-    int32_t *hInfo = static_cast<int32_t *>(cx.hSmall.p);
-    int st = upload_matrix(dA, ld, lu, n, n, n, cx.stream);
-    if (st == RLA_OK) st = getrf_launch<T>(n, dA, ld, dP, dInfo, cx.lu_ws, cx.stream);
-    if (st == RLA_OK) {
-        cudaError_t e = cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(cx.stream);
-        if (e != cudaSuccess) { note_cuda_error(e); st = RLA_ERR_CUDA; }
-    }
-    if (st == RLA_OK && *hInfo != 0) st = RLA_ERR_SINGULAR;
-    if (st == RLA_OK) {
-        st = download_matrix(lu, n, dA, ld, n, n, cx.stream);
+    auto body = [&]() -> int {
+        RLA_TRY(cx.dInfo.ensure(64));
+        RLA_TRY(cx.hSmall.ensure(64));
+        int32_t *dInfo = static_cast<int32_t *>(cx.dInfo.p);
+        int32_t *hInfo = static_cast<int32_t *>(cx.hSmall.p);
+        Stager &stg = cx.stager;
+        const bool pinned = !g_host_stage || host_is_pinned(lu);
+        RLA_TRY(stg.upload2d(dA, ld * sizeof(T), lu, n * sizeof(T), n * sizeof(T), n, pinned, cx.device, cx.stream));
+        size_t nev = 0;
+        const bool overlap = n >= 1024;            // below that one download after the factorisation is just as fast
+        LuRowsFinal rows_final = [&](int row0, int nrows, cudaStream_t st) -> int {
+            cudaEvent_t e;
+            RLA_TRY(cx.event(nev++, &e));
+            RLA_CUDA(cudaEventRecord(e, st));
+            RLA_CUDA(cudaStreamWaitEvent(cx.copy_out, e, 0));
+            return stg.download2d(lu + size_t(row0) * n, n * sizeof(T), dA + size_t(row0) * ld, ld * sizeof(T), n * sizeof(T),
+                                  size_t(nrows), pinned, cx.device, cx.copy_out);
+        };
+        RLA_TRY(getrf_launch<T>(n, dA, ld, dP, dInfo, cx.lu_ws, cx.stream, overlap ? &rows_final : nullptr));
+        RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
         static_assert(sizeof(size_t) == sizeof(int64_t), "LP64 expected");
-        if (st == RLA_OK) {
-            cudaError_t e = cudaMemcpyAsync(perm, dP, n * sizeof(int64_t), cudaMemcpyDeviceToHost, cx.stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(cx.stream);
-            if (e != cudaSuccess) { note_cuda_error(e); st = RLA_ERR_CUDA; }
-        }
-    }
+        RLA_CUDA(cudaMemcpyAsync(perm, dP, n * sizeof(int64_t), cudaMemcpyDeviceToHost, cx.stream));
+        RLA_CUDA(cudaStreamSynchronize(cx.stream));
+        const bool singular = *hInfo != 0;          // the reference drops the matrix: `lu` content is unspecified then
+        if (!overlap && !singular)
+            RLA_TRY(stg.download2d(lu, n * sizeof(T), dA, ld * sizeof(T), n * sizeof(T), n, pinned, cx.device, cx.copy_out));
+        RLA_CUDA(cudaStreamSynchronize(cx.copy_out));
+        RLA_TRY(stg.finish());
+        return singular ? RLA_ERR_SINGULAR : RLA_OK;
+    };
+    const int st = body();
+    if (st != RLA_OK && st != RLA_ERR_SINGULAR) (void)cx.stager.finish();
     if (keep_dev) {
         if (st == RLA_OK) {
             *keep_dev = dA;
             *keep_perm = dP;
             *keep_ld = ld;
         } else {
-            cudaFree(dA);
-            cudaFree(dP);
+            cudaFree(p1);
+            cudaFree(p2);
+            (void)cudaGetLastError();
         }
     }
     return st;
@@ -333,7 +417,7 @@ int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm,
 
 template <typename T>
 int getrs_core(size_t n, const T *dLU, size_t ld, const int64_t *dP, T *b) {
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     RLA_TRY(cx.dVec.ensure(n * sizeof(T)));
     RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(T)));
     RLA_TRY(cx.dInfo.ensure(64));
@@ -357,7 +441,7 @@ int getrs_host(size_t n, const T *lu, const size_t *perm, T *b) {
     if (n == 0) return RLA_OK;
     if (!lu || !perm || !b) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dPerm.ensure(n * sizeof(int64_t)));
@@ -373,7 +457,7 @@ int gemv_host(size_t m, size_t n, const T *a, ptrdiff_t rs, const T *x, T *y) {
     if (m == 0) return RLA_OK;
     if (!y || (n > 0 && (!a || !x)) || rs < ptrdiff_t(n)) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n ? n : 1, sizeof(T));
     RLA_TRY(cx.dA.ensure(m * ld * sizeof(T)));
     RLA_TRY(cx.dVec.ensure((n ? n : 1) * sizeof(T)));
@@ -392,7 +476,7 @@ int trsv_host(int lower, size_t n, const T *a, ptrdiff_t rs, T *x) {
     if (n == 0) return RLA_OK;
     if (!a || !x || rs < ptrdiff_t(n)) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dVec.ensure(n * sizeof(T)));
@@ -421,7 +505,7 @@ int potrf_host(size_t n, T *a) {
     if (n == 0) return RLA_OK;
     if (!a) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dChol.ensure(potrf_workspace_elems(n) * sizeof(T)));
@@ -444,7 +528,7 @@ int potrs_host(size_t n, const T *l, T *b) {
     if (n == 0) return RLA_OK;
     if (!l || !b) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dC.ensure(n * ld * sizeof(T)));
@@ -472,7 +556,7 @@ int potri_host(size_t n, const T *l, T *inv) {
     if (n == 0) return RLA_OK;
     if (!l || !inv) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dB.ensure(n * ld * sizeof(T)));
@@ -497,7 +581,7 @@ int getri_host(size_t n, const T *lu, const size_t *perm, T *inv) {
     if (n == 0) return RLA_OK;
     if (!lu || !perm || !inv) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dC.ensure(n * ld * sizeof(T)));
@@ -604,15 +688,19 @@ int rla_dgetrf_keep(size_t n, double *lu, size_t *perm, rla_lu_handle **out) {
     }
     int st = getrf_host<double>(n, lu, perm, &dA, &dP, &ld);
     if (st != RLA_OK) return st;
-    *out = new rla_lu_handle{n, ld, dA, dP, tl_ctx.device};
+    *out = new rla_lu_handle{n, ld, dA, dP, thread_ctx().device};
     return RLA_OK;
 }
 int rla_dlu_solve(const rla_lu_handle *h, double *b) {
     if (!h) return RLA_ERR_INVALID;
     if (h->n == 0) return RLA_OK;
     if (!b) return RLA_ERR_INVALID;
-    RLA_TRY(ensure_ctx());
-    return getrs_core<double>(h->n, h->lu, h->ld, h->perm, b);
+    int prev = -1;
+    if (cudaGetDevice(&prev) != cudaSuccess) { (void)cudaGetLastError(); prev = -1; }
+    RLA_TRY(ensure_ctx(h->device));                  // the factors live on the device that produced them
+    const int st = getrs_core<double>(h->n, h->lu, h->ld, h->perm, b);
+    if (prev >= 0 && prev != h->device) cudaSetDevice(prev);
+    return st;
 }
 void rla_lu_free(rla_lu_handle *h) {
     if (!h) return;
@@ -622,9 +710,15 @@ void rla_lu_free(rla_lu_handle *h) {
 }
 
 int rla_init(int device) { return ensure_ctx(device); }
-int rla_device_count(void) {
-    std::call_once(g_dev_once, probe_devices);
-    return g_dev_count;
+int rla_device_count(void) { return probe_device_count(); }
+int rla_set_devices(int n_gpus) { return multi_set_devices(n_gpus); }
+int rla_get_devices(void) { return multi_device_count(); }
+int rla_shutdown(void) {
+    // the calling thread's contexts (streams, events, device / pinned buffers, LU workspaces, staging rings) and the
+    // multi-device contexts; everything is rebuilt lazily by the next call
+    for (auto &c : tl_ctxs.per_dev) c.reset();
+    multi_release();
+    return RLA_OK;
 }
 int rla_dev_alloc(void **p, size_t bytes) {
     if (!p) return RLA_ERR_INVALID;
@@ -674,16 +768,16 @@ int rla_sgemm_dev(size_t m, size_t k, size_t n, float alpha, const float *a, siz
 }
 int rla_dgetrf_dev(size_t n, double *a, size_t ld, int64_t *d_perm, int32_t *d_info, void *stream) {
     RLA_TRY(ensure_ctx());
-    return getrf_launch<double>(n, a, ld, d_perm, d_info, tl_ctx.lu_ws, pick_stream(stream));
+    return getrf_launch<double>(n, a, ld, d_perm, d_info, thread_ctx().lu_ws, pick_stream(stream));
 }
 int rla_sgetrf_dev(size_t n, float *a, size_t ld, int64_t *d_perm, int32_t *d_info, void *stream) {
     RLA_TRY(ensure_ctx());
-    return getrf_launch<float>(n, a, ld, d_perm, d_info, tl_ctx.lu_ws, pick_stream(stream));
+    return getrf_launch<float>(n, a, ld, d_perm, d_info, thread_ctx().lu_ws, pick_stream(stream));
 }
 int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm, double *d_b, int32_t *d_info,
                    void *stream) {
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(double)));
     RLA_TRY(cx.dSync.ensure(64));
     return getrs_launch<double>(n, lu, ld, d_perm, d_b, static_cast<double *>(cx.dTrsv.p), d_info,
@@ -692,7 +786,7 @@ int rla_dgetrs_dev(size_t n, const double *lu, size_t ld, const int64_t *d_perm,
 int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, float *d_b, int32_t *d_info,
                    void *stream) {
     RLA_TRY(ensure_ctx());
-    Context &cx = tl_ctx;
+    Context &cx = thread_ctx();
     RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(float)));
     RLA_TRY(cx.dSync.ensure(64));
     return getrs_launch<float>(n, lu, ld, d_perm, d_b, static_cast<float *>(cx.dTrsv.p), d_info,
@@ -704,7 +798,7 @@ int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, si
                              void *d_plan, void *stream) {
     RLA_TRY(ensure_ctx());
     if (n > 0x3fffffffull || w == 0 || w > 256 || row0 + w > n) return RLA_ERR_INVALID;
-    return lu_factor_block_dev<double>(int(n), a_loc, ld, int(row0), int(lcol0), int(w), d_info, d_plan, tl_ctx.lu_ws,
+    return lu_factor_block_dev<double>(int(n), a_loc, ld, int(row0), int(lcol0), int(w), d_info, d_plan, thread_ctx().lu_ws,
                                        pick_stream(stream));
 }
 int rla_dlu_laswp_dev(double *a_loc, size_t ld, size_t w, const void *d_plan, const int32_t *d_info, size_t c0a,
@@ -740,6 +834,11 @@ int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, ui
     return fill_uniform_launch<float>(dst, rows, cols, ld, seed, offset, lo, scale, pick_stream(stream));
 }
 
+int rla_measure_peak(int kind, double *tflops) {
+    RLA_TRY(ensure_ctx());
+    return measure_peak(kind, tflops);
+}
+
 int rla_set_tuning(const char *key, int value) {
     if (!key) return RLA_ERR_INVALID;
     if (strcmp(key, "dgemm_cfg") == 0) {
@@ -763,6 +862,10 @@ int rla_set_tuning(const char *key, int value) {
     }
     if (strcmp(key, "lu_dbg") == 0) {
         g_lu_dbg = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "host_stage") == 0) {
+        g_host_stage = value ? 1 : 0;
         return RLA_OK;
     }
     if (strcmp(key, "lu_cluster") == 0) {

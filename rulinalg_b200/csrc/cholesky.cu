@@ -248,11 +248,11 @@ int potrf_launch(size_t n_, T *a, size_t ld, T *ws, int32_t *d_info, cudaStream_
     const int n = int(n_);
     RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
     if (n == 0) return RLA_OK;
-    static bool attr = false;
+    static DeviceOnce attr_once;
     const size_t panel_smem = size_t(CB + PANEL_ROWS) * CLD * sizeof(T);
-    if (!attr) {
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
         RLA_CUDA(cudaFuncSetAttribute(chol_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(panel_smem)));
-        attr = true;
+        attr_once.done(od_);
     }
     const size_t ldt = (n_ + 1) / 2 * 2;                    // transposed outer panel: CW x ldt
     T *t_outer = ws, *t_inner = ws + size_t(CW) * ldt;      // t_inner: CB x CW

@@ -4,6 +4,9 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#include <atomic>
+#include <functional>
+
 #include "../../include/rla_b200.h"
 
 namespace rla {
@@ -38,6 +41,27 @@ void note_launch(unsigned n = 1);
         ::rla::note_launch();                           \
     } while (0)
 
+// Per-device one-time setup.  cudaFuncSetAttribute (dynamic shared memory opt-in, cluster opt-in) and
+// occupancy answers are PER DEVICE: a process that drives several GPUs (rla_set_devices, or host threads
+// that rla_init different devices) must repeat them on each one.  Usage:
+//     static DeviceOnce once;  if (const int d = once.pending(); d >= 0) { ...cudaFuncSetAttribute...; once.done(d); }
+// Two threads racing on the same device both run the (idempotent) setup; nobody skips it.
+constexpr int RLA_MAX_DEVICES = 32;
+inline int current_device() {
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess) { (void)cudaGetLastError(); d = 0; }
+    return d & (RLA_MAX_DEVICES - 1);
+}
+struct DeviceOnce {
+    std::atomic<uint32_t> mask{0};
+    int pending() {              // current device id if its setup has not run yet, else -1
+        const int d = current_device();
+        return (mask.load(std::memory_order_acquire) & (1u << d)) ? -1 : d;
+    }
+    void done(int d) { mask.fetch_or(1u << d, std::memory_order_release); }
+};
+int device_num_sms();            // lu.cu: SM count of the current device (cached per device)
+
 // ---- kernel launchers (one per .cu) ---------------------------------------------------------
 int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda,
                  const double *b, size_t ldb, double beta, double *c, size_t ldc,
@@ -54,9 +78,12 @@ struct LuWorkspace {
     cudaStream_t side = nullptr;  // high-priority stream for the look-ahead panel factorisation
     cudaEvent_t ev_head = nullptr, ev_fact = nullptr;
 };
+// optional hook of getrf_launch: called (at enqueue time) when rows [row0, row0 + nrows) of the packed factors can no
+// longer change -- everything queued on `st` so far produces them; the host API starts their download there
+using LuRowsFinal = std::function<int(int row0, int nrows, cudaStream_t st)>;
 template <typename T>
 int getrf_launch(size_t n, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws,
-                 cudaStream_t st);
+                 cudaStream_t st, const LuRowsFinal *rows_final = nullptr);
 template <typename T>
 int getrs_launch(size_t n, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *ws3,
                  int32_t *d_info, int32_t *d_flags, cudaStream_t st);

@@ -293,14 +293,14 @@ __global__ void scale_c_kernel(size_t M, size_t N, T beta, T *C, size_t ldc) {
 template <class C, bool ALIGNED>
 int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
                double beta, double *c, size_t ldc, cudaStream_t st) {
-    static bool attr_set = false;
+    static DeviceOnce attr_once;
     const int tiles_m = int((m + C::BM - 1) / C::BM), tiles_n = int((n + C::BN - 1) / C::BN);
     const size_t tiles = size_t(tiles_m) * tiles_n;
     if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
-    if (!attr_set) {
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
         RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
         RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
-        attr_set = true;
+        attr_once.done(od_);
     }
     dgemm_dmma_kernel<C, ALIGNED><<<unsigned(tiles), C::THREADS, C::SMEM, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
                                                                                 beta, c, ldc, tiles_m, tiles_n);

@@ -1022,7 +1022,6 @@ int gemm_update<float>(size_t m, size_t k, size_t n, const float *a, size_t lda,
     return sgemm_launch(m, k, n, -1.f, a, lda, b, ldb, 1.f, c, ldc, st);
 }
 
-int g_num_sms = 0;
 unsigned long long *g_lu_trace = nullptr;
 int g_lu_gmax_ref();
 int g_lu_dbg_ref();
@@ -1038,11 +1037,6 @@ constexpr size_t SC_STATE = SC_PLAN + ((sizeof(LaswpPlan) + 255) / 256) * 256;
 constexpr size_t SC_TOTAL = SC_STATE + sizeof(PlanState) + 256;
 
 int ensure_workspace(LuWorkspace &ws, int n, cudaStream_t st) {
-    if (g_num_sms == 0) {
-        int dev = 0;
-        RLA_CUDA(cudaGetDevice(&dev));
-        RLA_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
-    }
     if (ws.ipiv_cap < size_t(2) * n) {                 // ipiv[n] + rowid[n]
         if (ws.ipiv) RLA_CUDA(cudaFree(ws.ipiv));
         ws.ipiv = nullptr;
@@ -1087,15 +1081,12 @@ PanelScratch scratch_view(LuWorkspace &ws) {
 template <typename T>
 int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t *ipiv, int32_t *d_info,
                  LaswpPlan *plan, cudaStream_t s) {
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    // largest cluster each device schedules for the cluster panel kernel (16 needs the non-portable opt-in)
+    static int cluster_max_dev[RLA_MAX_DEVICES];
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
-    // largest cluster this device schedules for the cluster panel kernel (16 needs the non-portable opt-in), once
-    static int cluster_max = -1;
-    if (cluster_max < 0) {
-        cluster_max = 0;
+        int cluster_max = 0;
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(CL_ROWS) * PLDS * sizeof(T))));
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         for (int cs = CL_MAX; cs >= 2; cs /= 2) {
@@ -1117,7 +1108,11 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
             }
             (void)cudaGetLastError();
         }
+        cluster_max_dev[od_] = cluster_max;
+        attr_once.done(od_);
     }
+    const int cluster_max = cluster_max_dev[current_device()];
+    const int num_sms = device_num_sms();
     PanelScratch sc = scratch_view(ws);
     sc.plan = plan;
     if (g_lu_dbg_ref() & 8) {
@@ -1152,8 +1147,8 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
                                         g_lu_dbg_ref()));
             note_launch();
         } else {
-        int G = min(min(g_num_sms - 1, g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
-        while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < g_num_sms - 1) ++G;
+        int G = min(min(num_sms - 1, g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
+        while (size_t((nrem + G - 1) / G) * PLDS * sizeof(T) > 200 * 1024 && G < num_sms - 1) ++G;
         int R = (nrem + G - 1) / G;
         size_t smem = size_t(R) * PLDS * sizeof(T);
         if (smem > 200 * 1024) return RLA_ERR_INVALID;   // n beyond ~58k rows per panel: not supported yet
@@ -1192,10 +1187,10 @@ int apply_laswp(T *a, size_t ld, int w, const LaswpPlan *plan, const int32_t *in
     const int ncols = (c1a - c0a) + (c1b - c0b);
     if (ncols <= 0) return RLA_OK;
     const size_t smem = size_t(2) * w * LASWP_CW * sizeof(T);
-    static bool attr = false;
-    if (!attr) {
+    static DeviceOnce attr_once;
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
         RLA_CUDA(cudaFuncSetAttribute(laswp_apply_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * LASWP_MAXJB * LASWP_CW * 8));
-        attr = true;
+        attr_once.done(od_);
     }
     const int blocks = (ncols + LASWP_CW - 1) / LASWP_CW;
     laswp_apply_kernel<T><<<blocks, LASWP_THREADS, smem, st>>>(a, ld, plan, info, c0a, c1a, c0b, c1b);
@@ -1230,6 +1225,27 @@ int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bi
 int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", 0/1): panels that fit one thread-block cluster use the DSMEM kernel
 namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } }
 
+int device_num_sms() {
+    static std::atomic<int> sms[RLA_MAX_DEVICES];
+    const int dev = current_device();
+    int v = sms[dev].load(std::memory_order_relaxed);
+    if (v == 0) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) { (void)cudaGetLastError(); v = 148; }
+        sms[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+void lu_workspace_release(LuWorkspace &ws) {
+    if (ws.ipiv) cudaFree(ws.ipiv);
+    if (ws.scratch) cudaFree(ws.scratch);
+    if (ws.side) cudaStreamDestroy(ws.side);
+    if (ws.ev_head) cudaEventDestroy(ws.ev_head);
+    if (ws.ev_fact) cudaEventDestroy(ws.ev_fact);
+    (void)cudaGetLastError();
+    ws = LuWorkspace();
+}
+
 size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
 int lu_trace_fetch(unsigned long long *host512) {
     if (!g_lu_trace) return RLA_ERR_INVALID;
@@ -1238,7 +1254,8 @@ int lu_trace_fetch(unsigned long long *host512) {
 }
 
 template <typename T>
-int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st) {
+int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st,
+                 const LuRowsFinal *rows_final) {
     if (n_ > 0x7fffffffull / 2) return RLA_ERR_INVALID;
     const int n = int(n_);
     RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
@@ -1275,8 +1292,13 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         rowid_apply_kernel<<<1, 256, 0, st>>>(plan, rowid, d_info);
         RLA_LAUNCHED();
         RLA_TRY(apply_laswp<T>(a, ld, w, plan, d_info, 0, J0, J0 + w, n, st));
-        if (J0 + w >= n) break;
+        if (J0 + w >= n) {
+            if (rows_final) RLA_TRY((*rows_final)(J0, w, st));
+            break;
+        }
         RLA_TRY(trsm_block<T>(a + size_t(J0) * ld + J0, ld, w, a + size_t(J0) * ld + J0 + w, ld, n - J0 - w, d_info, st));
+        // rows [J0, J0+w) are final from here on: later interchanges only touch rows below them
+        if (rows_final) RLA_TRY((*rows_final)(J0, w, st));
         const int next = J0 + w;
         const int wn = min(OUTER_W, n - next);
         if (lookahead && next + wn < n) {
@@ -1297,8 +1319,8 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
     return RLA_OK;
 }
 
-template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
-template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t);
+template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t, const LuRowsFinal *);
+template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t, const LuRowsFinal *);
 
 // PartialPivLu::inverse (lu.rs:251-285) as a blocked multi-RHS solve: X = U^-1 L^-1 P with all n unit vectors at once
 // (SURVEY 8f rank 1).  The reference performs n separate solves; this is 2n^3 flops on the GEMM kernels instead.
@@ -1398,5 +1420,8 @@ int lu_perm_from_rowid_dev(const int32_t *rowid, int64_t *perm, int n, const int
 template int lu_factor_block_dev<double>(int, double *, size_t, int, int, int, int32_t *, void *, LuWorkspace &, cudaStream_t);
 template int lu_laswp_dev<double>(double *, size_t, int, const void *, const int32_t *, int, int, int, int, cudaStream_t);
 template int lu_update_dev<double>(int, double *, size_t, int, int, const double *, size_t, int, int, const int32_t *, cudaStream_t);
+template int lu_factor_block_dev<float>(int, float *, size_t, int, int, int, int32_t *, void *, LuWorkspace &, cudaStream_t);
+template int lu_laswp_dev<float>(float *, size_t, int, const void *, const int32_t *, int, int, int, int, cudaStream_t);
+template int lu_update_dev<float>(int, float *, size_t, int, int, const float *, size_t, int, int, const int32_t *, cudaStream_t);
 
 }  // namespace rla

@@ -1,0 +1,437 @@
+// multi.cu -- one host process driving N GPUs behind the drop-in boundary (rla_set_devices).
+//
+// The reference call sites (src/matrix/mat_mul.rs:57-67, src/matrix/decomposition/lu.rs:163-195) can only ever reach
+// rla_dgemm / rla_dgetrf; after rla_set_devices(N) those two calls shard over the first N GPUs of the box:
+//
+//   GEMM  row panels: GPU g owns rows [g*mg, (g+1)*mg) of A and C.  B is the path's one exchange step.  Every column
+//         chunk of B is uploaded from the host by ONE GPU (chunks dealt round-robin, so the N PCIe links share the
+//         upload of B) and fanned out to the other N-1 over NVLink/NVSwitch by peer copies the receivers pull as soon
+//         as the owner's H2D has landed.  Uploads, pulls, DMMA kernels and downloads run as a 2-D wavefront per GPU
+//         (A row strips x B column chunks), all asynchronous, issued by the calling thread; every C element is one
+//         full-k product of the same kernel, so the result is bit-identical to the single-GPU call.
+//   LU    1D block-cyclic column blocks (block 256, owner(J) = J mod N); the factored panel travels by peer copies.
+//
+// There is no NCCL in this file: inside one process the exchange is peer memory (cudaMemcpyPeer semantics under UVA);
+// the one-process-per-GPU driver (rulinalg_b200/sharded*.py, bench.py under torchrun) uses NCCL for the same step.
+#include <memory>
+#include <mutex>
+
+#include "context.cuh"
+
+namespace rla {
+namespace {
+
+std::mutex g_multi_mu;                          // one multi-device operation (or reconfiguration) at a time
+std::atomic<int> g_ndev{1};
+std::unique_ptr<Context> g_mctx[RLA_MAX_DEVICES];
+
+struct DeviceRestore {
+    int dev = -1;
+    DeviceRestore() { if (cudaGetDevice(&dev) != cudaSuccess) { (void)cudaGetLastError(); dev = -1; } }
+    ~DeviceRestore() { if (dev >= 0) cudaSetDevice(dev); }
+};
+
+int device_ctx(int d, Context **out) {
+    RLA_CUDA(cudaSetDevice(d));
+    if (!g_mctx[d]) g_mctx[d].reset(new Context());
+    RLA_TRY(g_mctx[d]->init(d));
+    *out = g_mctx[d].get();
+    return RLA_OK;
+}
+
+}  // namespace
+
+int multi_device_count() { return g_ndev.load(std::memory_order_relaxed); }
+
+void multi_release() {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    for (auto &c : g_mctx) c.reset();
+}
+
+int multi_set_devices(int n) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    const int cnt = probe_device_count();
+    if (cnt == 0) return RLA_ERR_NO_DEVICE;
+    if (n < 1 || n > cnt) return RLA_ERR_INVALID;
+    DeviceRestore restore;
+    if (n > 1) {
+        for (int i = 0; i < n; ++i) {
+            if (!device_usable(i)) return RLA_ERR_NO_DEVICE;
+            RLA_CUDA(cudaSetDevice(i));
+            for (int j = 0; j < n; ++j) {
+                if (i == j) continue;
+                int can = 0;
+                RLA_CUDA(cudaDeviceCanAccessPeer(&can, i, j));
+                if (!can) return RLA_ERR_INVALID;             // the exchange step needs peer memory
+                const cudaError_t e = cudaDeviceEnablePeerAccess(j, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { note_cuda_error(e); return RLA_ERR_CUDA; }
+                (void)cudaGetLastError();
+            }
+        }
+    }
+    g_ndev.store(n, std::memory_order_relaxed);
+    return RLA_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// GEMM: C = alpha * A * B over N GPUs (beta == 0, unit column strides; the caller packed anything else).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T>
+int gemm_host_multi(size_t m, size_t k, size_t n, T alpha, const T *ha, size_t hrsa, const T *hb, size_t hrsb, T *hc,
+                    size_t hrsc, Stager &stg) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    DeviceRestore restore;
+    const int G = multi_device_count();
+    const size_t mg = ((m + G - 1) / G + 127) / 128 * 128;         // rows per GPU
+    const int Gu = int((m + mg - 1) / mg);                          // GPUs that get rows
+    const bool pin_a = host_is_pinned(ha), pin_b = host_is_pinned(hb), pin_c = host_is_pinned(hc);
+    const size_t lda = pad_ld(k, sizeof(T)), ldb = pad_ld(n, sizeof(T)), ldc = pad_ld(n, sizeof(T));
+
+    Context *cx[RLA_MAX_DEVICES];
+    T *dA[RLA_MAX_DEVICES], *dB[RLA_MAX_DEVICES], *dC[RLA_MAX_DEVICES];
+    size_t rows_of[RLA_MAX_DEVICES];
+    for (int g = 0; g < Gu; ++g) {
+        RLA_TRY(device_ctx(g, &cx[g]));
+        rows_of[g] = (size_t(g) + 1) * mg <= m ? mg : m - size_t(g) * mg;
+        RLA_TRY(cx[g]->dA.ensure(rows_of[g] * lda * sizeof(T)));
+        RLA_TRY(cx[g]->dB.ensure(k * ldb * sizeof(T)));
+        RLA_TRY(cx[g]->dC.ensure(rows_of[g] * ldc * sizeof(T)));
+        dA[g] = static_cast<T *>(cx[g]->dA.p);
+        dB[g] = static_cast<T *>(cx[g]->dB.p);
+        dC[g] = static_cast<T *>(cx[g]->dC.p);
+    }
+
+    // strips: ~512 rows / columns (the single-GPU pipeline's measured optimum), at least one B chunk per GPU
+    size_t S = (mg > n ? mg : n) / 512;
+    S = S < 4 ? 4 : (S > 32 ? 32 : S);
+    if (S < size_t(Gu)) S = size_t(Gu);
+    const size_t pm = ((mg + S - 1) / S + 127) / 128 * 128, pn = ((n + S - 1) / S + 127) / 128 * 128;
+    const size_t sm = (mg + pm - 1) / pm, sn = (n + pn - 1) / pn;
+    const size_t steps = sm > sn ? sm : sn;
+    enum { EV_IN = 0, EV_ROW, EV_COL, EV_P2P, EV_B, EV_PER_STEP };
+    auto ev = [&](int g, size_t st, int which, cudaEvent_t *e) { return cx[g]->event(EV_PER_STEP * st + which, e); };
+
+    for (size_t st = 0; st < steps; ++st) {
+        const size_t c0 = st * pn;
+        const size_t cols = st < sn ? (c0 + pn <= n ? pn : n - c0) : 0;
+        const int owner = int(st % size_t(Gu));
+        // ---- phase 1: host -> device.  The chunk's owner uploads it first (the others are waiting for it) ----
+        for (int g = 0; g < Gu; ++g) {
+            RLA_CUDA(cudaSetDevice(g));
+            cudaEvent_t e;
+            if (cols && g == owner) {
+                RLA_TRY(stg.upload2d(dB[g] + c0, ldb * sizeof(T), hb + c0, hrsb * sizeof(T), cols * sizeof(T), k, pin_b, g, cx[g]->copy_in));
+                RLA_TRY(ev(g, st, EV_B, &e));
+                RLA_CUDA(cudaEventRecord(e, cx[g]->copy_in));
+            }
+            const size_t r0 = st * pm;
+            const size_t rows = r0 < rows_of[g] ? (r0 + pm <= rows_of[g] ? pm : rows_of[g] - r0) : 0;
+            if (rows)
+                RLA_TRY(stg.upload2d(dA[g] + r0 * lda, lda * sizeof(T), ha + (size_t(g) * mg + r0) * hrsa, hrsa * sizeof(T),
+                                     k * sizeof(T), rows, pin_a, g, cx[g]->copy_in));
+            RLA_TRY(ev(g, st, EV_IN, &e));
+            RLA_CUDA(cudaEventRecord(e, cx[g]->copy_in));
+        }
+        // ---- phase 2: the exchange step.  Every other GPU pulls the chunk from its owner over NVLink ----
+        if (cols) {
+            cudaEvent_t eb;
+            RLA_TRY(ev(owner, st, EV_B, &eb));
+            for (int g = 0; g < Gu; ++g) {
+                if (g == owner) continue;
+                RLA_CUDA(cudaSetDevice(g));
+                RLA_CUDA(cudaStreamWaitEvent(cx[g]->p2p, eb, 0));
+                RLA_CUDA(cudaMemcpy2DAsync(dB[g] + c0, ldb * sizeof(T), dB[owner] + c0, ldb * sizeof(T), cols * sizeof(T), k,
+                                           cudaMemcpyDefault, cx[g]->p2p));
+                cudaEvent_t e;
+                RLA_TRY(ev(g, st, EV_P2P, &e));
+                RLA_CUDA(cudaEventRecord(e, cx[g]->p2p));
+            }
+        }
+        // ---- phase 3: every C tile that just became computable, then its download ----
+        for (int g = 0; g < Gu; ++g) {
+            RLA_CUDA(cudaSetDevice(g));
+            Context &c = *cx[g];
+            const size_t r0 = st * pm;
+            const size_t rows = r0 < rows_of[g] ? (r0 + pm <= rows_of[g] ? pm : rows_of[g] - r0) : 0;
+            const size_t ncols_avail = (st + 1 < sn ? (st + 1) * pn : n);
+            const size_t nrows_prev = r0 < rows_of[g] ? r0 : rows_of[g];
+            cudaEvent_t e_in, e_row, e_col, e_p2p = nullptr;
+            RLA_TRY(ev(g, st, EV_IN, &e_in));
+            RLA_TRY(ev(g, st, EV_ROW, &e_row));
+            RLA_TRY(ev(g, st, EV_COL, &e_col));
+            if (cols && g != owner) RLA_TRY(ev(g, st, EV_P2P, &e_p2p));
+            T *hcg = hc + size_t(g) * mg * hrsc;
+            if (rows) {
+                // row strip st against every chunk that has arrived (earlier chunks were waited for in earlier steps)
+                RLA_CUDA(cudaStreamWaitEvent(c.stream, e_in, 0));
+                if (e_p2p) RLA_CUDA(cudaStreamWaitEvent(c.stream, e_p2p, 0));
+                RLA_TRY(gemm_dev<T>(rows, k, ncols_avail, alpha, dA[g] + r0 * lda, lda, dB[g], ldb, T(0), dC[g] + r0 * ldc, ldc, c.stream));
+                RLA_CUDA(cudaEventRecord(e_row, c.stream));
+                RLA_CUDA(cudaStreamWaitEvent(c.copy_out, e_row, 0));
+                RLA_TRY(stg.download2d(hcg + r0 * hrsc, hrsc * sizeof(T), dC[g] + r0 * ldc, ldc * sizeof(T), ncols_avail * sizeof(T),
+                                       rows, pin_c, g, c.copy_out));
+            }
+            if (cols && nrows_prev) {
+                // column strip: the row strips before st against this step's chunk (disjoint C tiles, second stream)
+                RLA_CUDA(cudaStreamWaitEvent(c.stream2, e_in, 0));
+                if (e_p2p) RLA_CUDA(cudaStreamWaitEvent(c.stream2, e_p2p, 0));
+                RLA_TRY(gemm_dev<T>(nrows_prev, k, cols, alpha, dA[g], lda, dB[g] + c0, ldb, T(0), dC[g] + c0, ldc, c.stream2));
+                RLA_CUDA(cudaEventRecord(e_col, c.stream2));
+                RLA_CUDA(cudaStreamWaitEvent(c.copy_out, e_col, 0));
+                RLA_TRY(stg.download2d(hcg + c0, hrsc * sizeof(T), dC[g] + c0, ldc * sizeof(T), cols * sizeof(T), nrows_prev, pin_c,
+                                       g, c.copy_out));
+            }
+        }
+    }
+    for (int g = 0; g < Gu; ++g) {
+        RLA_CUDA(cudaSetDevice(g));
+        RLA_CUDA(cudaStreamSynchronize(cx[g]->copy_out));
+        RLA_CUDA(cudaStreamSynchronize(cx[g]->stream));
+        RLA_CUDA(cudaStreamSynchronize(cx[g]->stream2));
+        RLA_CUDA(cudaStreamSynchronize(cx[g]->p2p));      // nobody may still be reading this GPU's copy of B
+    }
+    return stg.finish();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// LU: PartialPivLu::decompose over N GPUs, 1D block-cyclic column blocks.  Global column block J (256
+// wide) lives on GPU J mod N at local columns [(J/N)*256, ...), every GPU stores its blocks side by side as an
+// n x ncl row-major matrix, so a panel is entirely local to its owner and the pivot search needs no communication.
+// Per block:  owner: factor in place (lu.cu panel kernels), pack [net row permutation | info | L11 over L21];
+//             others: pull that buffer over NVLink;  all: interchanges on the local columns outside the block,
+//             U12 = L11^-1 A12, A22 -= L21 U12 on the local blocks right of J.
+// Look-ahead 1: the owner of block J+1 updates that block's columns first and factors it on a high-priority side
+// stream while every GPU (itself included) runs the rest of block J's update; the pulls of panel J+1 hide under it.
+// The per-element operation order equals the single-GPU factorisation's, so the result is bit-identical to it.
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+constexpr size_t LU_BLOCK = 256;
+constexpr size_t LU_HEADER = 16384;      // >= lu_plan_bytes() + 8; a multiple of 256 so the panel stays 16-byte aligned
+
+struct LuDev {
+    Context *cx = nullptr;
+    cudaStream_t side = nullptr;         // look-ahead factorisation
+    size_t ncl = 0, ld = 0;              // local columns, row stride
+    void *a = nullptr;                   // local matrix
+    unsigned char *buf[2] = {nullptr, nullptr};
+};
+}  // namespace
+
+template <typename T>
+int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
+    std::lock_guard<std::mutex> lk(g_multi_mu);
+    DeviceRestore restore;
+    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
+    const int n = int(n_);
+    const int nb = int((n_ + LU_BLOCK - 1) / LU_BLOCK);
+    const int G = multi_device_count() < nb ? multi_device_count() : nb;
+    const bool pinned = host_is_pinned(lu);
+    const size_t plan_bytes = lu_plan_bytes();
+    const size_t info_off = (plan_bytes + 7) / 8 * 8;
+    if (info_off + 8 > LU_HEADER) return RLA_ERR_INVALID;
+    auto width = [&](int J) { return size_t(J) * LU_BLOCK + LU_BLOCK <= n_ ? LU_BLOCK : n_ - size_t(J) * LU_BLOCK; };
+    auto lcol0 = [&](int J) { return size_t(J / G) * LU_BLOCK; };
+
+    LuDev dv[RLA_MAX_DEVICES];
+    enum { EV_UP = 0, EV_HEAD, EV_READY, EV_PACKED0, EV_PACKED1, EV_PANEL0, EV_PANEL1, EV_DONE, EV_COUNT };
+    for (int g = 0; g < G; ++g) {
+        LuDev &d = dv[g];
+        RLA_TRY(device_ctx(g, &d.cx));
+        for (int J = g; J < nb; J += G) d.ncl += width(J);
+        d.ld = pad_ld(d.ncl, sizeof(T));
+        RLA_TRY(d.cx->dA.ensure(n_ * d.ld * sizeof(T)));
+        d.a = d.cx->dA.p;
+        for (int i = 0; i < 2; ++i) {
+            RLA_TRY(d.cx->dPanel[i].ensure(LU_HEADER + n_ * LU_BLOCK * sizeof(T)));
+            d.buf[i] = static_cast<unsigned char *>(d.cx->dPanel[i].p);
+        }
+        if (!d.cx->lu_ws.side) {
+            int lo = 0, hi = 0;
+            RLA_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            RLA_CUDA(cudaStreamCreateWithPriority(&d.cx->lu_ws.side, cudaStreamNonBlocking, hi));
+            RLA_CUDA(cudaEventCreateWithFlags(&d.cx->lu_ws.ev_head, cudaEventDisableTiming));
+            RLA_CUDA(cudaEventCreateWithFlags(&d.cx->lu_ws.ev_fact, cudaEventDisableTiming));
+        }
+        d.side = d.cx->lu_ws.side;
+    }
+    auto evt = [&](int g, int which, cudaEvent_t *e) { return dv[g].cx->event(size_t(which), e); };
+    auto info_ptr = [&](int g, int b) { return reinterpret_cast<int32_t *>(dv[g].buf[b] + info_off); };
+    auto panel_ptr = [&](int g, int b) { return reinterpret_cast<T *>(dv[g].buf[b] + LU_HEADER); };
+    auto A = [&](int g) { return static_cast<T *>(dv[g].a); };
+
+    // ---- upload: block columns in ascending order, every GPU over its own PCIe link ----
+    for (int J = 0; J < nb; ++J) {
+        const int g = J % G;
+        RLA_CUDA(cudaSetDevice(g));
+        RLA_TRY(stg.upload2d(A(g) + lcol0(J), dv[g].ld * sizeof(T), lu + size_t(J) * LU_BLOCK, n_ * sizeof(T), width(J) * sizeof(T), n_,
+                             pinned, g, dv[g].cx->copy_in));
+    }
+    for (int g = 0; g < G; ++g) {
+        RLA_CUDA(cudaSetDevice(g));
+        cudaEvent_t e;
+        RLA_TRY(evt(g, EV_UP, &e));
+        RLA_CUDA(cudaEventRecord(e, dv[g].cx->copy_in));
+        RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->stream, e, 0));
+    }
+    // row-origin vector (-> perm) lives on GPU 0
+    RLA_CUDA(cudaSetDevice(0));
+    RLA_TRY(dv[0].cx->dRowid.ensure(n_ * sizeof(int32_t)));
+    RLA_TRY(dv[0].cx->dPerm.ensure(n_ * sizeof(int64_t)));
+    RLA_TRY(dv[0].cx->hSmall.ensure(64));
+    int32_t *rowid = static_cast<int32_t *>(dv[0].cx->dRowid.p);
+    RLA_TRY(lu_rowid_init_dev(rowid, n, dv[0].cx->stream));
+
+    // owner side: factor block J in place and pack [plan | info | panel] into buf[b], all on `st`
+    auto factor_and_pack = [&](int J, int b, const int32_t *prev_info, cudaStream_t st) -> int {
+        const int g = J % G;
+        const size_t row0 = size_t(J) * LU_BLOCK, w = width(J), lc0 = lcol0(J);
+        int32_t *hinfo = info_ptr(g, b);
+        if (prev_info) RLA_CUDA(cudaMemcpyAsync(hinfo, prev_info, sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+        else RLA_CUDA(cudaMemsetAsync(hinfo, 0, sizeof(int32_t), st));
+        RLA_TRY(lu_factor_block_dev<T>(n, A(g), dv[g].ld, int(row0), int(lc0), int(w), hinfo, dv[g].buf[b], dv[g].cx->lu_ws, st));
+        RLA_CUDA(cudaMemcpy2DAsync(panel_ptr(g, b), w * sizeof(T), A(g) + row0 * dv[g].ld + lc0, dv[g].ld * sizeof(T), w * sizeof(T),
+                                   n_ - row0, cudaMemcpyDeviceToDevice, st));
+        return RLA_OK;
+    };
+    // receiver side: pull panel J from its owner's buf[b] once `packed` has fired; `ready` orders the pull after this
+    // GPU's last readers of its own buf[b]
+    auto pull = [&](int g, int J, int b, cudaEvent_t packed) -> int {
+        const int owner = J % G;
+        const size_t bytes = LU_HEADER + (n_ - size_t(J) * LU_BLOCK) * width(J) * sizeof(T);
+        cudaEvent_t ready, got;
+        RLA_TRY(evt(g, EV_READY, &ready));
+        RLA_CUDA(cudaEventRecord(ready, dv[g].cx->stream));
+        RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->p2p, ready, 0));
+        RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->p2p, packed, 0));
+        RLA_CUDA(cudaMemcpyPeerAsync(dv[g].buf[b], g, dv[owner].buf[b], owner, bytes, dv[g].cx->p2p));
+        RLA_TRY(evt(g, b ? EV_PANEL1 : EV_PANEL0, &got));
+        RLA_CUDA(cudaEventRecord(got, dv[g].cx->p2p));
+        return RLA_OK;
+    };
+    auto update = [&](int g, int J, int b, size_t c0, size_t c1) -> int {
+        if (c1 <= c0) return RLA_OK;
+        return lu_update_dev<T>(n, A(g), dv[g].ld, int(size_t(J) * LU_BLOCK), int(width(J)), panel_ptr(g, b), width(J), int(c0), int(c1),
+                                info_ptr(g, b), dv[g].cx->stream);
+    };
+    // first local column (on g) that belongs to a global block > J
+    auto first_after = [&](int g, int J) -> size_t {
+        const int Jn = J < g ? g : J + 1 + ((g - (J + 1)) % G + G) % G;     // smallest block index > J owned by g
+        return Jn < nb ? lcol0(Jn) : dv[g].ncl;
+    };
+
+    // block 0 has no predecessor
+    {
+        RLA_CUDA(cudaSetDevice(0));
+        RLA_TRY(factor_and_pack(0, 0, nullptr, dv[0].cx->stream));
+        cudaEvent_t packed;
+        RLA_TRY(evt(0, EV_PACKED0, &packed));
+        RLA_CUDA(cudaEventRecord(packed, dv[0].cx->stream));
+        for (int g = 1; g < G; ++g) {
+            RLA_CUDA(cudaSetDevice(g));
+            RLA_TRY(pull(g, 0, 0, packed));
+        }
+    }
+    for (int J = 0; J < nb; ++J) {
+        const int b = J & 1, owner = J % G;
+        const bool have_next = J + 1 < nb;
+        const int ow2 = (J + 1) % G;
+        const size_t w = width(J);
+        // ---- everyone: panel J has arrived -> interchanges on the local columns outside the block ----
+        for (int g = 0; g < G; ++g) {
+            RLA_CUDA(cudaSetDevice(g));
+            cudaStream_t st = dv[g].cx->stream;
+            if (g != owner) {
+                cudaEvent_t got;
+                RLA_TRY(evt(g, b ? EV_PANEL1 : EV_PANEL0, &got));
+                RLA_CUDA(cudaStreamWaitEvent(st, got, 0));
+            } else if (J > 0) {
+                cudaEvent_t packed;                       // factored on the owner's side stream
+                RLA_TRY(evt(g, b ? EV_PACKED1 : EV_PACKED0, &packed));
+                RLA_CUDA(cudaStreamWaitEvent(st, packed, 0));
+            }
+            if (g == 0) RLA_TRY(lu_rowid_apply_dev(dv[g].buf[b], rowid, info_ptr(g, b), st));
+            if (g == owner) {
+                const size_t lc0 = lcol0(J);
+                RLA_TRY(lu_laswp_dev<T>(A(g), dv[g].ld, int(w), dv[g].buf[b], info_ptr(g, b), 0, int(lc0), int(lc0 + w), int(dv[g].ncl), st));
+            } else {
+                RLA_TRY(lu_laswp_dev<T>(A(g), dv[g].ld, int(w), dv[g].buf[b], info_ptr(g, b), 0, int(dv[g].ncl), 0, 0, st));
+            }
+        }
+        // ---- the next block's owner: head update, then factor + pack on its side stream ----
+        cudaEvent_t packed_next = nullptr;
+        if (have_next) {
+            LuDev &o = dv[ow2];
+            RLA_CUDA(cudaSetDevice(ow2));
+            const size_t lo = first_after(ow2, J), wn = width(J + 1);      // lo = block J+1's first local column
+            RLA_TRY(update(ow2, J, b, lo, lo + wn));
+            cudaEvent_t head;
+            RLA_TRY(evt(ow2, EV_HEAD, &head));
+            RLA_CUDA(cudaEventRecord(head, o.cx->stream));
+            RLA_CUDA(cudaStreamWaitEvent(o.side, head, 0));                // also orders buf[1-b] after its local readers
+            for (int g = 0; g < G; ++g) {                                   // ... and after the GPUs that pulled panel J-1 from it
+                if (g == ow2 || J == 0 || (J - 1) % G != ow2) continue;
+                cudaEvent_t got;
+                RLA_TRY(evt(g, (1 - b) ? EV_PANEL1 : EV_PANEL0, &got));
+                RLA_CUDA(cudaStreamWaitEvent(o.side, got, 0));
+            }
+            RLA_TRY(factor_and_pack(J + 1, 1 - b, info_ptr(ow2, b), o.side));
+            RLA_TRY(evt(ow2, (1 - b) ? EV_PACKED1 : EV_PACKED0, &packed_next));
+            RLA_CUDA(cudaEventRecord(packed_next, o.side));
+        }
+        // ---- everyone: (the rest of) the update with panel J; the pulls of panel J+1 hide under it ----
+        for (int g = 0; g < G; ++g) {
+            RLA_CUDA(cudaSetDevice(g));
+            const size_t lo = first_after(g, J);
+            if (have_next && g == ow2) {
+                RLA_TRY(update(g, J, b, lo + width(J + 1), dv[g].ncl));
+            } else {
+                if (have_next) RLA_TRY(pull(g, J + 1, 1 - b, packed_next));
+                RLA_TRY(update(g, J, b, lo, dv[g].ncl));
+            }
+        }
+    }
+    // ---- perm, info, download ----
+    const int lastb = (nb - 1) & 1;
+    RLA_CUDA(cudaSetDevice(0));
+    {
+        Context &c0 = *dv[0].cx;
+        int64_t *dP = static_cast<int64_t *>(c0.dPerm.p);
+        int32_t *hInfo = static_cast<int32_t *>(c0.hSmall.p);
+        RLA_TRY(lu_perm_from_rowid_dev(rowid, dP, n, info_ptr(0, lastb), c0.stream));
+        RLA_CUDA(cudaMemcpyAsync(hInfo, info_ptr(0, lastb), sizeof(int32_t), cudaMemcpyDeviceToHost, c0.stream));
+        static_assert(sizeof(size_t) == sizeof(int64_t), "LP64 expected");
+        RLA_CUDA(cudaMemcpyAsync(perm, dP, n_ * sizeof(int64_t), cudaMemcpyDeviceToHost, c0.stream));
+    }
+    for (int g = 0; g < G; ++g) {
+        RLA_CUDA(cudaSetDevice(g));
+        cudaEvent_t done;
+        RLA_TRY(evt(g, EV_DONE, &done));
+        RLA_CUDA(cudaEventRecord(done, dv[g].cx->stream));
+        RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->copy_out, done, 0));
+    }
+    for (int J = 0; J < nb; ++J) {
+        const int g = J % G;
+        RLA_CUDA(cudaSetDevice(g));
+        RLA_TRY(stg.download2d(lu + size_t(J) * LU_BLOCK, n_ * sizeof(T), A(g) + lcol0(J), dv[g].ld * sizeof(T), width(J) * sizeof(T), n_,
+                               pinned, g, dv[g].cx->copy_out));
+    }
+    for (int g = 0; g < G; ++g) {
+        RLA_CUDA(cudaSetDevice(g));
+        RLA_CUDA(cudaStreamSynchronize(dv[g].cx->copy_out));
+        RLA_CUDA(cudaStreamSynchronize(dv[g].cx->stream));
+        RLA_CUDA(cudaStreamSynchronize(dv[g].side));
+        RLA_CUDA(cudaStreamSynchronize(dv[g].cx->p2p));
+    }
+    RLA_TRY(stg.finish());
+    return *static_cast<int32_t *>(dv[0].cx->hSmall.p) != 0 ? RLA_ERR_SINGULAR : RLA_OK;
+}
+
+template int getrf_host_multi<double>(size_t, double *, size_t *, Stager &);
+template int getrf_host_multi<float>(size_t, float *, size_t *, Stager &);
+
+template int gemm_host_multi<double>(size_t, size_t, size_t, double, const double *, size_t, const double *, size_t, double *,
+                                     size_t, Stager &);
+template int gemm_host_multi<float>(size_t, size_t, size_t, float, const float *, size_t, const float *, size_t, float *, size_t,
+                                    Stager &);
+
+}  // namespace rla

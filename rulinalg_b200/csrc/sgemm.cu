@@ -235,23 +235,23 @@ int sgemm_launch(size_t m, size_t k, size_t n, float alpha, const float *a, size
     if (m == 0 || n == 0) return RLA_OK;
     if (k == 0) return scale_c_launch<float>(m, n, beta, c, ldc, st);
     if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
-    static bool attr_set[2] = {false, false};
+    static DeviceOnce attr_once[2];
     const bool aligned = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
     const int tiles_m = int((m + BM - 1) / BM), tiles_n = int((n + BN - 1) / BN);
     const size_t tiles = size_t(tiles_m) * tiles_n;
     if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
     if (aligned) {
-        if (!attr_set[1]) {
+        if (const int od_ = attr_once[1].pending(); od_ >= 0) {
             RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-            attr_set[1] = true;
+            attr_once[1].done(od_);
         }
         sgemm_ffma_kernel<true><<<unsigned(tiles), THREADS, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
                                                                               beta, c, ldc, tiles_m, tiles_n);
     } else {
-        if (!attr_set[0]) {
+        if (const int od_ = attr_once[0].pending(); od_ >= 0) {
             RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-            attr_set[0] = true;
+            attr_once[0].done(od_);
         }
         sgemm_ffma_kernel<false><<<unsigned(tiles), THREADS, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
                                                                                beta, c, ldc, tiles_m, tiles_n);
