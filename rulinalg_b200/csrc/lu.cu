@@ -72,9 +72,13 @@ __device__ __forceinline__ void warp_argmax(unsigned long long &key, int &idx, u
 // Panel factorisation of A[J:n, J:J+jb].  Cooperative grid of G "row" CTAs + 1 "hub" CTA.
 // Row CTA b keeps rows [J + b*R, J + (b+1)*R) of the panel in shared memory.
 //
-// One grid-wide exchange per column, through 16-byte self-validating messages {payload, tag}
-// (tags are unique per (panel launch, column); a 16-byte aligned store is single-copy atomic, so no
-// fence is needed between a message and the data it announces -- every piece carries its own tag):
+// One grid-wide exchange per column, through 16-byte self-validating messages {payload, check}.  No fence sits between
+// a message and the data it announces because every piece validates itself: the check word carries a tag that is
+// unique per (panel launch, column) AND a hash of the payload word.  The PTX memory model only promises single-copy
+// atomicity for naturally aligned accesses of up to 8 bytes -- a 16-byte vector access is formally two 8-byte
+// accesses in unspecified order -- so a reader could in principle see a new check word next to an old payload; the
+// hash turns that torn view into "not there yet" (the reader polls again) instead of a silently wrong pivot row.
+// (On sm_100 an aligned 16-byte global access has never been observed to tear; over DSMEM it does, see below.)
 //   every row CTA publishes a candidate packet {|max| key, row index, tag} + the candidate row as 64
 //   tagged chunks, then reads ALL G packets with one whole warp (ceil(G/32) per lane), reduces them
 //   (every CTA reaches the same verdict), and fetches the winner's tagged row chunks.
@@ -94,6 +98,33 @@ __device__ __forceinline__ void msg_store(Msg *p, unsigned long long lo, unsigne
 }
 __device__ __forceinline__ void msg_load(const Msg *p, unsigned long long &lo, unsigned long long &hi) {
     asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(lo), "=l"(hi) : "l"(p) : "memory");
+}
+// 64 -> 32 bit mix of a payload word (two odd multipliers + xor-shift: any single-word change flips ~half the bits)
+__device__ __forceinline__ unsigned mix32(unsigned long long v) {
+    unsigned h = unsigned(v) * 0x9E3779B1u ^ unsigned(v >> 32) * 0x85EBCA6Bu;
+    return h ^ (h >> 15);
+}
+// value chunk: {bits, tag << 32 | mix32(bits)}
+__device__ __forceinline__ void chunk_store(Msg *p, unsigned long long bits, unsigned tag) {
+    msg_store(p, bits, ((unsigned long long)tag << 32) | mix32(bits));
+}
+__device__ __forceinline__ bool chunk_load(const Msg *p, unsigned tag, unsigned long long &bits) {
+    unsigned long long hi;
+    msg_load(p, bits, hi);
+    return hi == (((unsigned long long)tag << 32) | mix32(bits));
+}
+// candidate packet: {key, tag24 << 40 | mix16(key) << 24 | idx24}; idx24 = 0xffffff means "no candidate" (INT_MAX).
+// Tags stay below 2^24 (ensure_workspace re-zeroes the scratch before they would wrap), rows below 2^24 - 1.
+__device__ __forceinline__ void packet_store(Msg *p, unsigned long long key, int idx, unsigned tag) {
+    const unsigned long long i24 = idx == INT_MAX ? 0xffffffull : (unsigned long long)(unsigned)idx;
+    msg_store(p, key, ((unsigned long long)tag << 40) | ((unsigned long long)(mix32(key) & 0xffffu) << 24) | i24);
+}
+__device__ __forceinline__ bool packet_load(const Msg *p, unsigned tag, unsigned long long &key, int &idx) {
+    unsigned long long hi;
+    msg_load(p, key, hi);
+    const unsigned i24 = unsigned(hi) & 0xffffffu;
+    idx = i24 == 0xffffffu ? INT_MAX : int(i24);
+    return (hi >> 24) == (((unsigned long long)tag << 16) | (mix32(key) & 0xffffu));
 }
 __device__ __forceinline__ unsigned long long bits_of(double v) { return (unsigned long long)__double_as_longlong(v); }
 __device__ __forceinline__ unsigned long long bits_of(float v) { return (unsigned long long)__float_as_uint(v); }
@@ -117,9 +148,9 @@ struct PlanState {
     int of[LASWP_MAXJB];             // origin of far touched rows
 };
 struct PanelScratch {
-    Msg *packets;                    // [2][GMAX]       {bits(|max| as f64), idx | tag<<32}
-    Msg *rowbuf;                     // [2][GMAX][PW]   {bits(value), tag}
-    Msg *diagbuf;                    // [2][PW]         {bits(value), tag}
+    Msg *packets;                    // [2][GMAX]       {bits(|max| as f64), tag24 | hash16 | idx24}
+    Msg *rowbuf;                     // [2][GMAX][PW]   {bits(value), tag32 | hash32}
+    Msg *diagbuf;                    // [2][PW]         {bits(value), tag32 | hash32}
     unsigned long long *piv_log;     // [PW]            tag<<32 | pivot row (0xffffffff = singular), written by row CTA 0
     PlanState *state;
     LaswpPlan *plan;
@@ -262,7 +293,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int d = J + c;                       // global diagonal row of this column
         const int par = c & 1;
         const unsigned tag = tag_base + unsigned(c) + 1u;
-        const unsigned long long tag_hi = (unsigned long long)tag << 32;
+        const unsigned long long tag_hi = (unsigned long long)tag << 32;   // (pivot log: 8-byte entries, atomic as they are)
         const int lo = max(0, d - r0);             // first local row still active
         const bool owns_d = (d >= r0 && d < r1);
 
@@ -296,7 +327,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                 }
                 sh_idx = bidx;
                 // candidate packet first: it is what the hub is waiting for
-                msg_store(sc.packets + par * GMAX + b, bkey, (unsigned long long)(unsigned)bidx | tag_hi);
+                packet_store(sc.packets + par * GMAX + b, bkey, bidx, tag);
                 if (b == 0 && sc.trace) sc.trace[c * 8 + 1] = gtime();
             }
         }
@@ -305,9 +336,9 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         {
             const int li = sh_idx;
             if (li != INT_MAX && tid < jb)
-                msg_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(s[(li - r0) * PLDS + tid]), tag_hi);
+                chunk_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(s[(li - r0) * PLDS + tid]), tag);
             if (owns_d && tid >= 64 && tid < 64 + jb)
-                msg_store(sc.diagbuf + par * PW + (tid - 64), bits_of(s[(d - r0) * PLDS + (tid - 64)]), tag_hi);
+                chunk_store(sc.diagbuf + par * PW + (tid - 64), bits_of(s[(d - r0) * PLDS + (tid - 64)]), tag);
         }
         // ---- the verdict: every row CTA reads the G candidate packets itself with ONE whole warp (ceil(G/32)
         //      packets per lane; lanes past G duplicate packet G-1 so the warp is never partially active) ----
@@ -316,11 +347,9 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             int gi = INT_MAX, gw = 0;
             for (int base = 0; base < G; base += 32) {
                 const int q = min(base + lane, G - 1);
-                unsigned long long lo, hi;
-                do {
-                    msg_load(sc.packets + par * GMAX + q, lo, hi);
-                } while (unsigned(hi >> 32) != tag);
-                const int i1 = int(unsigned(hi & 0xffffffffull));
+                unsigned long long lo;
+                int i1;
+                while (!packet_load(sc.packets + par * GMAX + q, tag, lo, i1)) {}
                 if (lo > gk || (lo == gk && i1 < gi)) { gk = lo; gi = i1; gw = q; }
             }
             unsigned wm;
@@ -344,11 +373,9 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int prow_idx = sh_idx, win = sh_win;
         if (sh_sing) return;                       // uniform across the grid (every CTA reduces the same packets)
         if ((tid & ~31) < jb) {                   // whole warps poll (lanes past jb re-read chunk jb-1)
-            unsigned long long vlo, vhi;
+            unsigned long long vlo;
             const Msg *src = sc.rowbuf + size_t(par * GMAX + win) * PW + min(tid, jb - 1);
-            do {
-                msg_load(src, vlo, vhi);
-            } while (unsigned(vhi >> 32) != tag);
+            while (!chunk_load(src, tag, vlo)) {}
             T v;
             from_bits(vlo, v);
             if (tid < jb) prow_s[tid] = v;
@@ -357,11 +384,9 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         if (prow_idx != d) {                       // swap rows d <-> prow_idx inside the panel
             if (owns_d && tid < jb) s[(d - r0) * PLDS + tid] = prow_s[tid];
             if (prow_idx >= r0 && prow_idx < r1 && tid >= 64 && ((tid - 64) & ~31) < jb) {
-                unsigned long long vlo, vhi;
+                unsigned long long vlo;
                 const Msg *src = sc.diagbuf + par * PW + min(tid - 64, jb - 1);
-                do {
-                    msg_load(src, vlo, vhi);
-                } while (unsigned(vhi >> 32) != tag);
+                while (!chunk_load(src, tag, vlo)) {}
                 T v;
                 from_bits(vlo, v);
                 if (tid - 64 < jb) s[(prow_idx - r0) * PLDS + (tid - 64)] = v;
@@ -1053,8 +1078,9 @@ int ensure_workspace(LuWorkspace &ws, int n, cudaStream_t st) {
         ws.tag = 0;
         RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
     }
-    // tags are unique per (launch, column) for the lifetime of the scratch buffer; re-zero before wrap-around
-    if (ws.tag > 0xffffffffu - 2u * unsigned(n) - 16u) {
+    // tags are unique per (launch, column) for the lifetime of the scratch buffer and stay below 2^24 (the candidate
+    // packets carry 24 tag bits); re-zero before they would wrap
+    if (ws.tag > 0xffffffu - 2u * unsigned(n) - 16u) {
         RLA_CUDA(cudaMemsetAsync(ws.scratch, 0, SC_TOTAL, st));
         ws.tag = 0;
     }
