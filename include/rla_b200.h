@@ -200,6 +200,12 @@ RLA_API size_t rla_lu_plan_bytes(void);
 /* development aid: with rla_set_tuning("lu_dbg", 8) the four inner panels of the last outer block record 64 x 8 words
  * each (globaltimer stamps in slots 0..6, the pivot row in slot 7); copies 4 x 512 words to host2048 */
 RLA_API int rla_debug_lu_trace(unsigned long long *host2048);
+/* test aid: the panel kernel forms its multipliers a / pivot from a correctly rounded reciprocal (five FMAs instead of an
+ * IEEE division per row); this compares that against the IEEE division over `count` pseudo-random operand pairs
+ * (mode 0: arbitrary bit patterns incl. NaN / Inf / subnormals; mode 1: LU-like, |a| <= |b|) and returns the number
+ * of results that differ in any bit.  Must be 0. */
+RLA_API int rla_debug_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count,
+                               unsigned long long *mismatches);
 RLA_API int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w,
                              int32_t *d_info, void *d_plan, void *stream);
 RLA_API int rla_dlu_laswp_dev(double *a_loc, size_t ld, size_t w, const void *d_plan, const int32_t *d_info,

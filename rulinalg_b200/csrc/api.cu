@@ -794,6 +794,11 @@ int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
 }
 size_t rla_lu_plan_bytes(void) { return lu_plan_bytes(); }
 int rla_debug_lu_trace(unsigned long long *host512) { return lu_trace_fetch(host512); }
+int rla_debug_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count, unsigned long long *mismatches) {
+    if (!mismatches) return RLA_ERR_INVALID;
+    RLA_TRY(ensure_ctx());
+    return lu_divcheck(f32, mode, seed, count, mismatches);
+}
 int rla_dlu_factor_block_dev(size_t n, double *a_loc, size_t ld, size_t row0, size_t lcol0, size_t w, int32_t *d_info,
                              void *d_plan, void *stream) {
     RLA_TRY(ensure_ctx());
@@ -869,7 +874,8 @@ int rla_set_tuning(const char *key, int value) {
         return RLA_OK;
     }
     if (strcmp(key, "lu_cluster") == 0) {
-        g_lu_cluster = value ? 1 : 0;
+        if (value < 0 || value > 2) return RLA_ERR_INVALID;
+        g_lu_cluster = value;
         return RLA_OK;
     }
     return RLA_ERR_INVALID;

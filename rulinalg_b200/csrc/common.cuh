@@ -108,6 +108,7 @@ int potri_launch(size_t n, const T *l, size_t ld, T *x, size_t ldx, T *m, int64_
 template <typename T>
 int gemv_launch(size_t m, size_t n, const T *a, size_t lda, const T *x, T *y, cudaStream_t st);
 size_t lu_plan_bytes();
+int lu_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count, unsigned long long *mismatches);
 int lu_trace_fetch(unsigned long long *host512);
 template <typename T>
 int lu_factor_block_dev(int n, T *a_loc, size_t ld, int row0, int lcol0, int w, int32_t *d_info, void *d_plan,

@@ -57,6 +57,27 @@ __device__ __forceinline__ float div_rn(float a, float b) { return __fdiv_rn(a, 
 __device__ __forceinline__ unsigned long long key_of(double absval) {
     return absval < 0.0 ? 0ull : (unsigned long long)__double_as_longlong(absval);
 }
+// Same result, shorter dependency chain in the common case: when a single lane holds the maximal HIGH word (random data:
+// practically always) it is the winner and one redux + one ballot + two shuffles decide; otherwise the full reduction runs.
+__device__ __forceinline__ void warp_argmax_fast(unsigned long long &key, int &idx, unsigned &winner_mask) {
+    const unsigned hi = unsigned(key >> 32);
+    const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
+    const unsigned top = __ballot_sync(0xffffffffu, hi == mhi && idx != INT_MAX);
+    if (top != 0u && (top & (top - 1u)) == 0u) {          // exactly one lane (warp-uniform)
+        const int src = __ffs(top) - 1;
+        key = __shfl_sync(0xffffffffu, key, src);
+        idx = __shfl_sync(0xffffffffu, idx, src);
+        winner_mask = top;
+        return;
+    }
+    const unsigned lo = unsigned(key);
+    const unsigned mlo = __reduce_max_sync(0xffffffffu, hi == mhi ? lo : 0u);
+    const bool t2 = (hi == mhi) && (lo == mlo);
+    const int midx = __reduce_min_sync(0xffffffffu, t2 ? idx : INT_MAX);
+    winner_mask = __ballot_sync(0xffffffffu, t2 && idx == midx);
+    key = ((unsigned long long)mhi << 32) | mlo;
+    idx = midx;
+}
 __device__ __forceinline__ void warp_argmax(unsigned long long &key, int &idx, unsigned &winner_mask) {
     const unsigned hi = unsigned(key >> 32), lo = unsigned(key);
     const unsigned mhi = __reduce_max_sync(0xffffffffu, hi);
@@ -845,6 +866,551 @@ lu_panel_cluster_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int 
 }
 
 // -------------------------------------------------------------------------------------------
+// Cluster panel kernel, second generation ("pushed rows").  Same data placement idea as lu_panel_cluster_kernel
+// (panel in the registers of one thread-block cluster, implicit pivoting, identical arithmetic and verdicts =>
+// bit-identical factors), but the per-column dependency chain is cut from five CTA barriers + a DSMEM round trip
+// (~1.5 us per column) to two one-way DSMEM hops and no CTA-wide barrier at all:
+//   * a row lives in the two lanes 2j, 2j+1 of ONE warp (lane parity h holds the columns of parity h), so the value
+//     in the next pivot column travels between them by shuffle and both know at once whether their row is the
+//     warp's candidate;
+//   * only column c+1 is brought up to date before the pivot search (one mul + one sub); the candidates are reduced
+//     (redux.sync), posted to warp 0 with bar.arrive, and the rest of the rank-1 update runs in the shadow of the
+//     exchange;
+//   * every warp stages its own candidate row (post-update) in a per-warp slot, speculatively; warp 0 of every CTA
+//     reduces the 16 warp candidates, sends the CTA's packet to every CTA (st.async + mbarrier complete_tx, as
+//     before) and reaches the verdict; warp 0 of the WINNER CTA then PUSHES the winner's staged row + a 16-byte
+//     verdict header into every CTA's pivot-row buffer as 16-byte st.async chunks that complete tx bytes on the
+//     destination's row mbarrier.  Nobody pulls, nobody waits on a CTA barrier: all 512 threads of every CTA sleep
+//     on the row mbarrier and wake with the pivot row in their shared memory;
+//   * the IEEE division per row (the multiplier) left the critical path: the staged row carries RN(1/candidate),
+//     computed in the shadow of the exchange, and every row forms colc / pivot from it with five FMAs (div_via_rcp:
+//     correctly rounded, bit-identical to the division).
+// Buffers (slots, pivot rows, packets, mbarriers) alternate by column parity; a CTA can be at most one column ahead.
+// -------------------------------------------------------------------------------------------
+// Correctly rounded a / b from a correctly rounded reciprocal y = RN(1/b) that is computed ONCE per pivot (by the lane
+// that stages the candidate row, in the shadow of the exchange) instead of a full IEEE division per row on the
+// critical path:  q0 = a*y;  q1 = q0 + (a - b*q0)*y  (faithful);  q2 = q1 + (a - b*q1)*y = RN(a/b)  (Markstein's
+// theorem: a faithful quotient corrected once with the exactly computed residual and the correctly rounded reciprocal
+// is the correctly rounded quotient).  The residuals are exact FMAs as long as nothing under- or overflows, which the
+// exponent guard ensures; everything else (zeros, subnormals, huge / tiny magnitudes, Inf, NaN) takes the IEEE division.
+// Bit-identity with __ddiv_rn / __fdiv_rn is asserted over 2^32 operand pairs in tests (rla_debug_divcheck).
+__device__ __forceinline__ double rcp_rn(double b) { return __drcp_rn(b); }
+__device__ __forceinline__ float rcp_rn(float b) { return __frcp_rn(b); }
+__device__ __forceinline__ bool div_fast_ok(double a, double b) {
+    const unsigned ea = (unsigned(__double2hiint(a)) >> 20) & 0x7ffu, eb = (unsigned(__double2hiint(b)) >> 20) & 0x7ffu;
+    return ea - 0x300u < 0x200u && eb - 0x300u < 0x200u;          // both in [2^-255, 2^256)
+}
+__device__ __forceinline__ bool div_fast_ok(float a, float b) {
+    const unsigned ea = (__float_as_uint(a) >> 23) & 0xffu, eb = (__float_as_uint(b) >> 23) & 0xffu;
+    return ea - 0x60u < 0x40u && eb - 0x60u < 0x40u;              // both in [2^-31, 2^33)
+}
+__device__ __forceinline__ double div_via_rcp(double a, double b, double y) {
+    if (!div_fast_ok(a, b)) return __ddiv_rn(a, b);
+    const double q0 = __dmul_rn(a, y);
+    const double q1 = __fma_rn(__fma_rn(-b, q0, a), y, q0);
+    return __fma_rn(__fma_rn(-b, q1, a), y, q1);
+}
+__device__ __forceinline__ float div_via_rcp(float a, float b, float y) {
+    if (!div_fast_ok(a, b)) return __fdiv_rn(a, b);
+    const float q0 = __fmul_rn(a, y);
+    const float q1 = __fmaf_rn(__fmaf_rn(-b, q0, a), y, q0);
+    return __fmaf_rn(__fmaf_rn(-b, q1, a), y, q1);
+}
+// brute-force check of the above against the IEEE division (development / test aid)
+template <typename T>
+__global__ void divcheck_kernel(unsigned long long seed, unsigned long long per_thread, int mode, unsigned long long *mismatches) {
+    unsigned long long bad = 0;
+    unsigned long long x = splitmix64(seed + (unsigned long long)(blockIdx.x * blockDim.x + threadIdx.x) * 0x9E3779B97F4A7C15ull);
+    for (unsigned long long i = 0; i < per_thread; ++i) {
+        x = splitmix64(x);
+        const unsigned long long r1 = x;
+        x = splitmix64(x);
+        const unsigned long long r2 = x;
+        T a, b;
+        if (sizeof(T) == 8) {
+            double da, db;
+            if (mode == 0) {            // arbitrary bit patterns (all exponents, NaN, Inf, subnormals)
+                da = __longlong_as_double((long long)r1);
+                db = __longlong_as_double((long long)r2);
+            } else {                    // LU-like: |a| <= |b|, magnitudes spread over 2^-40 .. 2^8, random mantissas and signs
+                const int eb = 1023 - 40 + int((r2 >> 52) % 48);
+                db = __longlong_as_double((long long)((r2 & 0x800fffffffffffffull) | ((unsigned long long)eb << 52)));
+                const int ea = eb - int((r1 >> 52) % 60);
+                da = __longlong_as_double((long long)((r1 & 0x800fffffffffffffull) | ((unsigned long long)(ea > 1 ? ea : 1) << 52)));
+            }
+            a = T(da); b = T(db);
+        } else {
+            float fa, fb;
+            if (mode == 0) {
+                fa = __uint_as_float(unsigned(r1));
+                fb = __uint_as_float(unsigned(r2));
+            } else {
+                const int eb = 127 - 20 + int((r2 >> 32) % 28);
+                fb = __uint_as_float((unsigned(r2) & 0x807fffffu) | (unsigned(eb) << 23));
+                const int ea = eb - int((r1 >> 32) % 30);
+                fa = __uint_as_float((unsigned(r1) & 0x807fffffu) | (unsigned(ea > 1 ? ea : 1) << 23));
+            }
+            a = T(fa); b = T(fb);
+        }
+        const T want = div_rn(a, b);
+        const T got = div_via_rcp(a, b, rcp_rn(b));
+        const bool same = (sizeof(T) == 8) ? (__double_as_longlong(double(want)) == __double_as_longlong(double(got)))
+                                           : (__float_as_uint(float(want)) == __float_as_uint(float(got)));
+        const bool both_nan = (want != want) && (got != got);
+        if (!same && !both_nan) ++bad;
+    }
+    if (bad) atomicAdd(mismatches, bad);
+}
+
+template <int V>
+struct IC { static constexpr int value = V; };           // integral constant for generic-lambda dispatch
+
+template <typename T>
+struct RowLay {
+    static constexpr int HALF = PW / 2;                       // columns per lane
+    static constexpr int PADE = 16 / int(sizeof(T));          // 16 bytes between the two halves: the lanes of a pair hit
+    static constexpr int ODD0 = HALF + PADE;                  //   different banks when they read "their" half
+    static constexpr int ELEMS = 2 * HALF + PADE;             // staged row: [even columns][pad: RN(1/candidate)][odd columns]
+    static constexpr int RCP = HALF;                          // the reciprocal of the candidate value sits in the pad
+    static constexpr int TOTAL = ELEMS + 16 / int(sizeof(T)); // + verdict header {pivot position, singular}
+    static constexpr unsigned ROW_BYTES = unsigned(ELEMS * sizeof(T));
+    static constexpr unsigned TX_BYTES = ROW_BYTES + 16u;
+};
+constexpr int C2_BAR_CAND = 1, C2_BAR_STAGED = 2;             // named barriers (0 is __syncthreads)
+
+__device__ __forceinline__ void named_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "n"(CL_THREADS) : "memory"); }
+__device__ __forceinline__ void named_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "n"(CL_THREADS) : "memory"); }
+// trace stamps (lu_dbg bit 3; separate instantiation so the production kernel carries none of it): warp 0 of CTA
+// rank 0, slot s of column tc_
+#define C2TRACE(tc_, slot)                                              \
+    do {                                                                \
+        if (TRACE && trace && rank == 0 && warp == 0) {                 \
+            const unsigned long long t_ = gtime();                      \
+            if (lane == 0) trace[(tc_) * 8 + (slot)] = t_;              \
+            __syncwarp();                                               \
+        }                                                               \
+    } while (0)
+
+// stamps of three other warps of CTA rank 0 (pages 1..3 of the trace buffer): when do THEY see the row, post, stage
+#define C2TRACE_W(tc_, slot)                                                                   \
+    do {                                                                                       \
+        if (TRACE && trace && rank == 0 && (warp == 5 || warp == 10 || warp == 15)) {          \
+            const unsigned long long t_ = gtime();                                             \
+            if (lane == 0) trace[(warp / 5) * 512 + (tc_) * 8 + (slot)] = t_;                  \
+            __syncwarp();                                                                      \
+        }                                                                                      \
+    } while (0)
+
+// Shared state of the exchange.  One struct so the out-of-line chain functions below take a single pointer: the column
+// loop is unrolled 8x (static register indices) and everything inlined into it is replicated 8 times -- with the chain
+// inline the kernel was 186 KB of code and ran out of instruction cache (every column step fetched its instructions
+// from L2: 2.4 us per column).
+template <typename T>
+struct C2Shared {
+    Msg cand[2][CL_MAX];                                 // [parity][source rank], written remotely (st.async)
+    unsigned long long bar_pk[2];                        // packets: 1 arrival (mine) + 16*CS tx bytes
+    unsigned long long bar_row[2];                       // pivot row: 1 arrival (mine) + TX_BYTES
+    T slot[2][CL_THREADS / 32][RowLay<T>::ELEMS];        // [parity][warp]: the warp's candidate row
+    T prow[2][RowLay<T>::TOTAL];                         // [parity]: the pivot row + verdict header (pushed)
+    unsigned long long red_key[CL_THREADS / 32];
+    int red_idx[CL_THREADS / 32];
+    unsigned long long best[2];                          // [parity]: running maximum of the warps' candidate keys (staging filter)
+};
+
+// warp 0, first half: reduce the 16 warp candidates, send the CTA's candidate to every CTA.  Returns the warp that
+// holds the CTA's candidate.
+template <typename T>
+__device__ __noinline__ void c2_chain_send(C2Shared<T> *sh, int par, unsigned rank, unsigned CS) {
+    constexpr int NW = CL_THREADS / 32;
+    const int lane = threadIdx.x & 31;
+    named_sync(C2_BAR_CAND);                 // every warp's candidate is in red_key / red_idx
+    // reset the staging filter of the NEXT column: its last users passed this barrier two columns ago, its next users
+    // wake only after the row that this CTA's packet (sent below) helps to decide has travelled back
+    if (lane == 0) sh->best[par ^ 1] = 0ull;
+    unsigned long long ckey = (lane < NW) ? sh->red_key[lane] : 0ull;
+    int cidx = (lane < NW) ? sh->red_idx[lane] : INT_MAX;
+    unsigned wmk;
+    warp_argmax_fast(ckey, cidx, wmk);
+    const int ww = wmk ? __ffs(wmk) - 1 : 0; // lane index == warp index of the CTA's candidate
+    if (lane == 0) mbar_expect_tx(smem_u32(&sh->bar_pk[par]), 16u * CS);
+    __syncwarp();
+    if (unsigned(lane) < CS)
+        st_async_v2(mapa(smem_u32(&sh->cand[par][rank]), unsigned(lane)), ckey,
+                    (unsigned long long)(unsigned)cidx | ((unsigned long long)(unsigned)ww << 32),
+                    mapa(smem_u32(&sh->bar_pk[par]), unsigned(lane)));
+}
+// warp 0, second half: verdict; the winner CTA pushes [row | header] into every CTA's pivot-row buffer as 16-byte
+// st.async chunks (lane l sends chunk l to every CTA).  (cp.async.bulk was measured here first: no faster.)
+template <typename T, bool TRACE>
+__device__ __noinline__ void c2_chain_finish(C2Shared<T> *sh, int cn, int par, unsigned rank, unsigned CS, unsigned long long *trace) {
+    using RL = RowLay<T>;
+    const int lane = threadIdx.x & 31, warp = 0;
+    mbar_wait(smem_u32(&sh->bar_pk[par]), unsigned(cn >> 1) & 1u);
+    C2TRACE(cn, 3);
+    const int q = min(lane, int(CS) - 1);
+    unsigned long long gk = ((volatile Msg *)&sh->cand[par][q])->lo;
+    const unsigned long long hi = ((volatile Msg *)&sh->cand[par][q])->hi;
+    int gi = int(unsigned(hi));
+    int gslot = int(unsigned(hi >> 32)), gw = q;
+    if (unsigned(lane) >= CS) { gk = 0ull; gi = INT_MAX; }   // lanes past the cluster size carry no candidate
+    unsigned wm2;
+    warp_argmax_fast(gk, gi, wm2);
+    const int src_lane = wm2 ? __ffs(wm2) - 1 : 0;
+    gw = __shfl_sync(0xffffffffu, gw, src_lane);
+    gslot = __shfl_sync(0xffffffffu, gslot, src_lane);
+    const int sing = (T(__longlong_as_double((long long)gk)) < Eps<T>::v()) ? 1 : 0;   // lu.rs:179-183
+    if (lane == 0) mbar_expect_tx(smem_u32(&sh->bar_row[par]), RL::TX_BYTES);
+    if (unsigned(gw) != rank) {              // not my row: nothing to wait for (the barrier still needs my arrival)
+        named_arrive(C2_BAR_STAGED);
+        C2TRACE(cn, 4);
+        C2TRACE(cn, 5);
+        return;
+    }
+    named_sync(C2_BAR_STAGED);               // every warp of this CTA has staged its candidate row
+    C2TRACE(cn, 4);
+    {
+        constexpr int NCH = int(RL::TX_BYTES / 16);                         // 34 (f64) / 18 (f32)
+        const unsigned long long *src = reinterpret_cast<const unsigned long long *>(&sh->slot[par][gslot][0]);
+#pragma unroll
+        for (int ch0 = 0; ch0 < NCH; ch0 += 32) {
+            const int ch = ch0 + lane;
+            if (ch < NCH) {
+                unsigned long long v0, v1;
+                if (ch < NCH - 1) { v0 = src[2 * ch]; v1 = src[2 * ch + 1]; }
+                else { v0 = (unsigned long long)(unsigned)gi; v1 = (unsigned long long)(unsigned)sing; }
+                const unsigned dst = smem_u32(&sh->prow[par][0]) + 16u * unsigned(ch), bar = smem_u32(&sh->bar_row[par]);
+                for (unsigned r = 0; r < CS; ++r) st_async_v2(mapa(dst, r), v0, v1, mapa(bar, r));
+            }
+        }
+    }
+    C2TRACE(cn, 5);
+}
+__device__ __noinline__ void fold_pivot_ool(int *od, int *fr, int *of, int *nf, int base, int w, int d, int p) {
+    int v = *nf;
+    fold_pivot(od, fr, of, v, base, w, d, p, int(threadIdx.x & 31));
+    *nf = v;
+}
+
+template <typename T, bool TRACE>
+__global__ void __launch_bounds__(CL_THREADS, 1)
+lu_panel_cluster2_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int32_t *__restrict__ ipiv,
+                         int32_t *__restrict__ info, PanelScratch sc, int J0, int w, int dbg) {
+    if (*info != 0) return;   // written by an earlier kernel => uniform over the cluster
+    using RL = RowLay<T>;
+    extern __shared__ __align__(16) unsigned char panel_smem[];   // [CL_ROWS][PLDS] staging for coalesced panel load / store
+    T *stg = reinterpret_cast<T *>(panel_smem);
+    __shared__ __align__(16) C2Shared<T> shx;
+    C2Shared<T> *sh = &shx;
+    __shared__ int sh_nt;
+    __shared__ PlanState st;                                      // CTA rank 0: the outer block's plan state
+    __shared__ int od_l[PW], fr_l[PW], of_l[PW];                  // the panel's own net permutation
+    __shared__ int rows_l[2 * PW], org_l[2 * PW];
+    __shared__ int posv[CL_ROWS];                                 // final position of my rows (write-back)
+    __shared__ int nf_sh[2];                                      // far-row counts of the two folds
+    unsigned long long *const trace = sc.trace;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const unsigned rank = cluster_ctarank(), CS = cluster_nctarank();
+    if (tid == 0) {
+        mbar_init(smem_u32(&sh->bar_pk[0]), 1);
+        mbar_init(smem_u32(&sh->bar_pk[1]), 1);
+        mbar_init(smem_u32(&sh->bar_row[0]), 1);
+        mbar_init(smem_u32(&sh->bar_row[1]), 1);
+        sh->best[0] = sh->best[1] = 0ull;
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    cluster_sync_all();
+
+    // lane pair (2j, 2j+1) = one row; lane parity h holds columns 2k + h, k = 0..31, in registers for the whole panel.
+    // Rows never move: `pos` is the row's position in the reference's (physically swapped) ordering.
+    const int lrow = tid >> 1, h = tid & 1;
+    const int r0 = J + int(rank) * R;
+    const int nrows = max(0, min(n, r0 + R) - r0);
+    const bool has_row = lrow < nrows;
+    int pos = r0 + lrow;
+    bool active = has_row;
+    T a[RL::HALF];
+    if (jb == PW) {
+#pragma unroll 8
+        for (int idx = tid; idx < nrows * PW; idx += CL_THREADS)
+            stg[(idx >> 6) * PLDS + (idx & 63)] = A[size_t(r0 + (idx >> 6)) * ld + J + (idx & 63)];
+    } else {
+        for (int idx = tid; idx < nrows * jb; idx += CL_THREADS) {
+            const int r = idx / jb, cc = idx - r * jb;
+            stg[r * PLDS + cc] = A[size_t(r0 + r) * ld + J + cc];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RL::HALF; ++k) a[k] = (has_row && 2 * k + h < jb) ? stg[lrow * PLDS + 2 * k + h] : T(0);
+
+    constexpr int NW = CL_THREADS / 32, LOCAL_FOLD_WARP = NW - 1, PLAN_FOLD_WARP = NW - 2;
+    if (warp == LOCAL_FOLD_WARP) {
+        for (int i = lane; i < jb; i += 32) od_l[i] = i;
+        if (lane == 0) nf_sh[0] = 0;
+    } else if (warp == PLAN_FOLD_WARP && rank == 0) {
+        if (J == J0) {
+            for (int i = lane; i < w; i += 32) st.od[i] = i;
+            if (lane == 0) nf_sh[1] = 0;
+        } else {
+            for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                st.od[i] = sc.state->od[i];
+                st.fr[i] = sc.state->fr[i];
+                st.of[i] = sc.state->of[i];
+            }
+            if (lane == 0) nf_sh[1] = sc.state->nf;
+        }
+    }
+    __syncwarp();
+
+    // ---- the pieces of one column step -----------------------------------------------------------------------
+    // candidates of column cn from `val` (valid in the lanes with h == (cn & 1)); posts the warp's candidate
+    auto post_candidate = [&](int cn, T val, unsigned &wm) {
+        unsigned long long bkey = 0ull;
+        int bidx = INT_MAX;
+        if (active && h == (cn & 1)) {
+            const T av = fabs(val);
+            if (av == av) { bkey = key_of(double(av)); bidx = pos; }                     // a NaN never wins ...
+            else if (pos == J + cn) { bkey = key_of(CUDART_INF); bidx = pos; }             // ... unless it is the diagonal (lu.rs:170-171)
+        }
+        warp_argmax_fast(bkey, bidx, wm);
+        // staging filter: only a warp whose candidate is not already beaten by an earlier poster stages its row (the CTA's
+        // eventual winner -- maximal key, lowest position among equals -- always passes: nothing posted can exceed it)
+        unsigned long long seen = 0ull;
+        if (lane == 0) {
+            sh->red_key[warp] = bkey;
+            sh->red_idx[warp] = bidx;
+            seen = atomicMax(&sh->best[cn & 1], bkey);
+        }
+        seen = __shfl_sync(0xffffffffu, seen, 0);
+        if (bkey < seen) wm = 0u;
+    };
+    // my (post-update) row into the warp's slot if it is the warp's candidate
+    // (the lane that holds the candidate VALUE also leaves RN(1/value) in the pad: the next column's multipliers are
+    // formed from it, see div_via_rcp)
+    auto stage_row = [&](int par, unsigned wm, int cn, T val) {
+        if ((wm >> (lane & ~1)) & 3u) {
+            T *dst = &sh->slot[par][warp][h * RL::ODD0];
+#pragma unroll
+            for (int k = 0; k < RL::HALF; k += int(16 / sizeof(T))) {
+                if constexpr (sizeof(T) == 8) *reinterpret_cast<double2 *>(dst + k) = make_double2(a[k], a[k + 1]);
+                else *reinterpret_cast<float4 *>(dst + k) = make_float4(a[k], a[k + 1], a[k + 2], a[k + 3]);
+            }
+            if (h == (cn & 1)) sh->slot[par][warp][RL::RCP] = rcp_rn(val);
+        }
+        __syncwarp();
+    };
+
+    // ---- prologue: candidates of column 0 from the raw panel ----
+    {
+        unsigned wm;
+        post_candidate(0, a[0], wm);
+        if (warp == 0) c2_chain_send<T>(sh, 0, rank, CS); else named_arrive(C2_BAR_CAND);
+        stage_row(0, wm, 0, a[0]);
+        if (warp == 0) c2_chain_finish<T, TRACE>(sh, 0, 0, rank, CS, trace); else named_arrive(C2_BAR_STAGED);
+    }
+    T colc;                                      // my row's value in the current pivot column (both lanes of the pair)
+    T a1;                                        // my value in the NEXT pivot column before this column's update (its holder lane)
+    {
+        const T mine = a[0], other = __shfl_xor_sync(0xffffffffu, mine, 1);
+        colc = (h == 0) ? mine : other;
+        a1 = a[0];                               // column 1 = element 0 of the odd lane
+    }
+
+    bool singular = false;
+    // One pivot column.  S8 = c mod 8 is a compile-time constant so that every register index below is static:
+    // column c = 2*kc + s with kc = 4*gidx + sub0, s = S8 & 1, sub0 = S8 >> 1 static and gidx = c / 8 warp-uniform.
+    auto column_step = [&](auto S8, const int c8) {
+        constexpr int s8 = decltype(S8)::value;
+        constexpr int s = s8 & 1, sub0 = s8 >> 1;
+        const int c = c8 + s8;
+        const int d = J + c;
+        const int par = c & 1;
+        const int gidx = c8 >> 3;
+        const int kc = 4 * gidx + sub0;
+        // ---- the pivot row of column c (and the verdict) has been pushed into prow[par] ----
+        mbar_wait(smem_u32(&sh->bar_row[par]), unsigned(c >> 1) & 1u);
+        C2TRACE(c, 0);
+        C2TRACE_W(c, 0);
+        const T *u = sh->prow[par];
+        const ulonglong2 hv = *reinterpret_cast<const ulonglong2 *>(&sh->prow[par][RL::ELEMS]);
+        const int p = int(unsigned(hv.x));
+        if (hv.y != 0ull) {                                 // |pivot| < eps: uniform over the cluster
+            if (rank == 0 && tid == 0) *info = d + 1;
+            singular = true;
+            return;
+        }
+        if (rank == 0 && tid == 0) ipiv[d] = p;
+        // bookkeeping of the interchange d <-> p: the picked row retires to position d, the row at d moves to p
+        if (pos == p) { active = false; pos = d; }
+        else if (pos == d) pos = p;
+        const T *uh = u + h * RL::ODD0;                    // my half of the pivot row: uh[k] = U[c][2k + h]
+        const T piv = u[s * RL::ODD0 + kc];
+        const T m = active ? div_via_rcp(colc, piv, u[RL::RCP]) : T(0);   // == colc / piv, IEEE-rounded (both lanes compute it)
+        const bool more = c + 1 < jb;
+        unsigned wm = 0;
+        T nxt = T(0);
+        if (more) {
+            // ---- column c+1 first (one mul + one sub from the value captured one step earlier), candidates, post ----
+            const int k1 = kc + s;                          // column c+1 = 2*k1 + (1 - s)
+            if (active && h == 1 - s) nxt = sub_rn(a1, mul_rn(m, uh[k1]));
+            const T other = __shfl_xor_sync(0xffffffffu, nxt, 1);
+            colc = (h == 1 - s) ? nxt : other;              // both lanes: my row's value in column c+1
+            post_candidate(c + 1, nxt, wm);
+            C2TRACE(c + 1, 6);
+            C2TRACE_W(c + 1, 1);
+            if (warp == 0) c2_chain_send<T>(sh, par ^ 1, rank, CS); else named_arrive(C2_BAR_CAND);
+            C2TRACE(c + 1, 1);
+        }
+        // ---- the rank-1 update with mul, sub, in the shadow of the exchange.  Groups of 4 right of the pivot group:
+        //      one indexed jump, then straight-line code.  The pivot group (static sub0) looks at the lane parity, stores
+        //      the multiplier in the lane that holds column c, and captures column c+2 for the next step. ----
+        if (active) {
+            auto upd4 = [&](auto G) {
+                constexpr int k = 4 * decltype(G)::value;
+                if constexpr (sizeof(T) == 8) {
+                    const double2 u0 = *reinterpret_cast<const double2 *>(uh + k), u1 = *reinterpret_cast<const double2 *>(uh + k + 2);
+                    a[k] = sub_rn(a[k], mul_rn(m, T(u0.x)));
+                    a[k + 1] = sub_rn(a[k + 1], mul_rn(m, T(u0.y)));
+                    a[k + 2] = sub_rn(a[k + 2], mul_rn(m, T(u1.x)));
+                    a[k + 3] = sub_rn(a[k + 3], mul_rn(m, T(u1.y)));
+                } else {
+                    const float4 uu = *reinterpret_cast<const float4 *>(uh + k);
+                    a[k] = sub_rn(a[k], mul_rn(m, T(uu.x)));
+                    a[k + 1] = sub_rn(a[k + 1], mul_rn(m, T(uu.y)));
+                    a[k + 2] = sub_rn(a[k + 2], mul_rn(m, T(uu.z)));
+                    a[k + 3] = sub_rn(a[k + 3], mul_rn(m, T(uu.w)));
+                }
+            };
+            switch (gidx) {
+                case 0: upd4(IC<1>{}); [[fallthrough]];
+                case 1: upd4(IC<2>{}); [[fallthrough]];
+                case 2: upd4(IC<3>{}); [[fallthrough]];
+                case 3: upd4(IC<4>{}); [[fallthrough]];
+                case 4: upd4(IC<5>{}); [[fallthrough]];
+                case 5: upd4(IC<6>{}); [[fallthrough]];
+                case 6: upd4(IC<7>{}); [[fallthrough]];
+                default: break;
+            }
+            auto pivgroup = [&](auto G) {
+                constexpr int g = decltype(G)::value;
+#pragma unroll
+                for (int sub = sub0 + 1; sub < 4; ++sub) a[4 * g + sub] = sub_rn(a[4 * g + sub], mul_rn(m, uh[4 * g + sub]));
+                constexpr int k = 4 * g + sub0;
+                if constexpr (s == 0) a[k] = h ? sub_rn(a[k], mul_rn(m, uh[k])) : m;   // column c is even: the odd lane still updates 2k+1
+                else { if (h) a[k] = m; }                                               // column c is odd: it is the odd lane's own
+                if constexpr (k + 1 < RL::HALF) a1 = a[k + 1];                           // column c+2 = 2(kc+1) + s, after this update
+            };
+            switch (gidx) {
+                case 0: pivgroup(IC<0>{}); break;
+                case 1: pivgroup(IC<1>{}); break;
+                case 2: pivgroup(IC<2>{}); break;
+                case 3: pivgroup(IC<3>{}); break;
+                case 4: pivgroup(IC<4>{}); break;
+                case 5: pivgroup(IC<5>{}); break;
+                case 6: pivgroup(IC<6>{}); break;
+                default: pivgroup(IC<7>{}); break;
+            }
+        }
+        if (more) {
+            stage_row(par ^ 1, wm, c + 1, nxt);
+            C2TRACE(c + 1, 2);
+            C2TRACE_W(c + 1, 2);
+            if (warp == 0) c2_chain_finish<T, TRACE>(sh, c + 1, par ^ 1, rank, CS, trace); else named_arrive(C2_BAR_STAGED);
+        }
+        // ---- the hub's bookkeeping, off the critical path ----
+        if (warp == LOCAL_FOLD_WARP) fold_pivot_ool(od_l, fr_l, of_l, &nf_sh[0], J, jb, d, p);
+        else if (warp == PLAN_FOLD_WARP && rank == 0) fold_pivot_ool(st.od, st.fr, st.of, &nf_sh[1], J0, w, d, p);
+    };
+    for (int c8 = 0; c8 < jb && !singular; c8 += 8) {
+        column_step(IC<0>{}, c8);
+        if (c8 + 1 < jb && !singular) column_step(IC<1>{}, c8);
+        if (c8 + 2 < jb && !singular) column_step(IC<2>{}, c8);
+        if (c8 + 3 < jb && !singular) column_step(IC<3>{}, c8);
+        if (c8 + 4 < jb && !singular) column_step(IC<4>{}, c8);
+        if (c8 + 5 < jb && !singular) column_step(IC<5>{}, c8);
+        if (c8 + 6 < jb && !singular) column_step(IC<6>{}, c8);
+        if (c8 + 7 < jb && !singular) column_step(IC<7>{}, c8);
+    }
+
+
+    if (!singular) {
+        // write the panel back permuted: registers -> shared memory -> coalesced rows at their final positions
+        if (has_row) {
+#pragma unroll
+            for (int k = 0; k < RL::HALF; ++k) stg[lrow * PLDS + 2 * k + h] = a[k];
+            if (h == 0) posv[lrow] = pos;
+        }
+        if (warp == PLAN_FOLD_WARP && rank == 0) {
+            if (J + jb != J0 + w) {
+                for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                    sc.state->od[i] = st.od[i];
+                    sc.state->fr[i] = st.fr[i];
+                    sc.state->of[i] = st.of[i];
+                }
+                if (lane == 0) sc.state->nf = nf_sh[1];
+            } else {
+                const int nt = w + nf_sh[1];
+                if (lane == 0) sc.plan->nt = nt;
+                for (int i = lane; i < nt; i += 32) {
+                    sc.plan->rows[i] = (i < w) ? J0 + i : st.fr[i - w];
+                    sc.plan->origin[i] = (i < w) ? st.od[i] : st.of[i - w];
+                }
+            }
+        }
+        if (warp == LOCAL_FOLD_WARP) {
+            const int nt = jb + nf_sh[0];
+            for (int i = lane; i < nt; i += 32) {
+                rows_l[i] = (i < jb) ? J + i : fr_l[i - jb];
+                org_l[i] = (i < jb) ? od_l[i] : of_l[i - jb];
+            }
+            if (lane == 0) sh_nt = nt;
+        }
+        __syncthreads();
+        if (jb == PW) {
+#pragma unroll 8
+            for (int idx = tid; idx < nrows * PW; idx += CL_THREADS)
+                A[size_t(posv[idx >> 6]) * ld + J + (idx & 63)] = stg[(idx >> 6) * PLDS + (idx & 63)];
+        } else {
+            for (int idx = tid; idx < nrows * jb; idx += CL_THREADS) {
+                const int r = idx / jb, cc = idx - r * jb;
+                A[size_t(posv[r]) * ld + J + cc] = stg[r * PLDS + cc];
+            }
+        }
+        if (!(dbg & 1)) {
+            const int na = J - J0, ncols = na + (J0 + w - J - jb);     // columns [J0, J) and [J + jb, J0 + w)
+            const int cpc = (ncols + int(CS) - 1) / int(CS);
+            const int c_lo = int(rank) * cpc, c_hi = min(ncols, c_lo + cpc);
+            const int nt = sh_nt;
+            for (int g0 = c_lo; g0 < c_hi; g0 += CL_GC) {             // uniform per CTA
+                T v[4];
+                bool mv[4];
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int e = tid + CL_THREADS * uu, i = e / CL_GC, t2 = g0 + (e % CL_GC);
+                    mv[uu] = i < nt && t2 < c_hi && org_l[i] != i;
+                    if (mv[uu]) {
+                        const int col = (t2 < na) ? J0 + t2 : J + jb + (t2 - na);
+                        v[uu] = A[size_t(rows_l[org_l[i]]) * ld + col];
+                    }
+                }
+                __syncthreads();                                        // every source is read before any destination is written
+#pragma unroll
+                for (int uu = 0; uu < 4; ++uu) {
+                    const int e = tid + CL_THREADS * uu, i = e / CL_GC, t2 = g0 + (e % CL_GC);
+                    if (mv[uu]) {
+                        const int col = (t2 < na) ? J0 + t2 : J + jb + (t2 - na);
+                        A[size_t(rows_l[i]) * ld + col] = v[uu];
+                    }
+                }
+            }
+        }
+    }
+    cluster_sync_all();       // remote shared memory must stay alive while anyone may still write into it
+}
+
+// -------------------------------------------------------------------------------------------
 // laswp for a whole outer block: interchanges (J+k <-> ipiv[J+k]), k = 0..jb-1 (jb <= 256), applied
 // to the columns left and right of the block as ONE gather instead of jb dependent swaps.
 //   plan kernel (one warp): simulate the interchanges on indices.  "Touched" rows: index i < jb ->
@@ -1115,6 +1681,10 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
         int cluster_max = 0;
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(CL_ROWS) * PLDS * sizeof(T))));
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster2_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(CL_ROWS) * PLDS * sizeof(T))));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster2_kernel<T, false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster2_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(CL_ROWS) * PLDS * sizeof(T))));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster2_kernel<T, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         for (int cs = CL_MAX; cs >= 2; cs /= 2) {
             cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(cs);
@@ -1169,8 +1739,15 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
             at[0].val.clusterDim.z = 1;
             cfg.attrs = at;
             cfg.numAttrs = 1;
-            RLA_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<T>, a, ld, n, j, jb, R, ipiv, d_info, sc, J0, w,
-                                        g_lu_dbg_ref()));
+            if (g_lu_cluster_ref() == 2 && sc.trace)
+                RLA_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_cluster2_kernel<T, true>, a, ld, n, j, jb, R, ipiv, d_info, sc, J0, w,
+                                            g_lu_dbg_ref()));
+            else if (g_lu_cluster_ref() == 2)
+                RLA_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_cluster2_kernel<T, false>, a, ld, n, j, jb, R, ipiv, d_info, sc, J0, w,
+                                            g_lu_dbg_ref()));
+            else
+                RLA_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_cluster_kernel<T>, a, ld, n, j, jb, R, ipiv, d_info, sc, J0, w,
+                                            g_lu_dbg_ref()));
             note_launch();
         } else {
         int G = min(min(num_sms - 1, g_lu_gmax_ref()), max(1, (nrem + 63) / 64));
@@ -1248,7 +1825,7 @@ int g_lu_gmax = 32;           // rla_set_tuning("lu_gmax", v): cap on the grid p
                               // rows fit in shared memory).  The panel is latency-bound, its CTAs only take SMs from the overlapped
                               // Schur update: tools/lu_gmax_sweep.py, n = 16384: 120.9 / 128.0 / 133.1 ms at 32 / 112 / 147
 int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bit0: hub skips row swaps, bit2: no look-ahead)
-int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", 0/1): panels that fit one thread-block cluster use the DSMEM kernel
+int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", v): 0 = always the grid-wide panel kernel; 1 (default) = panels that fit one thread-block cluster use the DSMEM pull kernel; 2 = the pushed-row cluster kernel (experimental: bit-identical, measured slower)
 namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } }
 
 int device_num_sms() {
@@ -1273,6 +1850,21 @@ void lu_workspace_release(LuWorkspace &ws) {
 }
 
 size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
+
+// development / test aid: div_via_rcp against the IEEE division over `count` pseudo-random operand pairs
+int lu_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count, unsigned long long *mismatches) {
+    unsigned long long *d = nullptr;
+    RLA_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    RLA_CUDA(cudaMemset(d, 0, sizeof(unsigned long long)));
+    const unsigned blocks = 148 * 8, threads = 256;
+    const unsigned long long per = (count + blocks * threads - 1) / (blocks * threads);
+    if (f32) divcheck_kernel<float><<<blocks, threads>>>(seed, per, mode, d);
+    else divcheck_kernel<double><<<blocks, threads>>>(seed, per, mode, d);
+    RLA_LAUNCHED();
+    RLA_CUDA(cudaMemcpy(mismatches, d, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+    cudaFree(d);
+    return RLA_OK;
+}
 int lu_trace_fetch(unsigned long long *host512) {
     if (!g_lu_trace) return RLA_ERR_INVALID;
     RLA_CUDA(cudaMemcpy(host512, g_lu_trace, 4 * 64 * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));

@@ -385,13 +385,62 @@ def test_lu_cluster_panel_identical_to_grid_panel(rla, oracle, dtype):
         sing[:, 130] = 0.0                      # exact zero column -> DivByZero at column 130 in both kernels
         cases.append(sing)
         for a in cases:
-            g, c = factor(a, 0), factor(a, 1)
-            assert g[2] == c[2]
-            if g[2] == 0:
-                assert np.array_equal(g[1], c[1])
-                assert np.array_equal(g[0], c[0], equal_nan=True)
+            g = factor(a, 0)
+            for mode in (1, 2):                 # DSMEM pull kernel; pushed-row kernel
+                c = factor(a, mode)
+                assert g[2] == c[2], (a.shape, mode)
+                if g[2] == 0:
+                    assert np.array_equal(g[1], c[1]), (a.shape, mode)
+                    assert np.array_equal(g[0], c[0], equal_nan=True), (a.shape, mode)
     finally:
-        l.rla_set_tuning(b"lu_cluster", 1)
+        l.rla_set_tuning(b"lu_cluster", LU_CLUSTER_DEFAULT)
+
+
+LU_CLUSTER_DEFAULT = 1
+
+
+@pytest.mark.parametrize("f32", [0, 1])
+@pytest.mark.parametrize("mode", [0, 1])
+def test_multiplier_division_is_ieee(rla, f32, mode):
+    """The pushed-row panel kernel forms m = a / pivot from a correctly rounded reciprocal + five FMAs (lu.cu
+    div_via_rcp); the reference divides (lu.rs:606).  2^32 operand pairs per case (arbitrary bit patterns incl. NaN, Inf,
+    subnormals; and LU-like |a| <= |b|): every result must equal the IEEE division bit for bit."""
+    bad = C.c_uint64(1)
+    assert rla.lib().rla_debug_divcheck(f32, mode, 20240 + mode, 1 << 32, C.byref(bad)) == 0
+    assert bad.value == 0
+
+
+def test_lu_panel_kernels_randomized_stress(rla, oracle):
+    """a long randomized A/B run of the three panel kernels (grid exchange through L2 with hashed
+    self-validating messages; cluster pull; cluster push).  60 seeded matrices with sizes that hit every cluster
+    size and ragged panels, each factored by all three: bit-identical factors, permutations, status."""
+    import torch
+    l = rla.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    rng = np.random.default_rng(2024)
+
+    def factor(a_dev0, mode):
+        assert l.rla_set_tuning(b"lu_cluster", mode) == 0
+        n = a_dev0.shape[0]
+        a = a_dev0.clone()
+        perm = torch.empty(n, dtype=torch.int64, device="cuda")
+        info = torch.zeros(1, dtype=torch.int32, device="cuda")
+        rla.check(l.rla_dgetrf_dev(n, a.data_ptr(), n, perm.data_ptr(), info.data_ptr(), s))
+        return a, perm, info
+
+    try:
+        for trial in range(60):
+            n = int(rng.choice([130, 256, 300, 511, 640, 1000, 1500, 2048, 2500, 3333, 4096]))
+            a0 = torch.from_numpy(oracle.fill_uniform((n, n), 9000 + trial, np.float64, lo=-0.5, scale=1.0)).cuda()
+            g = factor(a0, 0)
+            for mode in (1, 2):
+                c = factor(a0, mode)
+                torch.cuda.synchronize()
+                assert int(g[2].item()) == int(c[2].item()) == 0
+                assert torch.equal(g[1], c[1]), (trial, n, mode)
+                assert torch.equal(g[0], c[0]), (trial, n, mode)
+    finally:
+        l.rla_set_tuning(b"lu_cluster", LU_CLUSTER_DEFAULT)
 
 
 def lu_checks(rla, oracle, a, f, ref=None):
