@@ -16,6 +16,7 @@
 namespace rla {
 
 extern int g_dgemm_cfg;   // dgemm.cu
+extern int g_sgemm_cfg;   // sgemm.cu
 extern int g_lu_gmax, g_lu_dbg, g_lu_cluster;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 int g_host_gemm_s = 0;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline; 0 = auto (~512-row strips)
@@ -849,6 +850,11 @@ int rla_set_tuning(const char *key, int value) {
     if (strcmp(key, "dgemm_cfg") == 0) {
         if (value < -1 || value > 7) return RLA_ERR_INVALID;
         g_dgemm_cfg = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "sgemm_cfg") == 0) {
+        if (value < -1 || value > 1) return RLA_ERR_INVALID;
+        g_sgemm_cfg = value;
         return RLA_OK;
     }
     if (strcmp(key, "lu_gmax") == 0) {

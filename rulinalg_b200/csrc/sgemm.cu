@@ -22,8 +22,11 @@
 namespace rla {
 namespace {
 
-constexpr int BM = 128, BN = 128, BK = 16, THREADS = 256;
-constexpr int LDT = BM + 4;    // padded row of the k-major A tile and of the B tile (floats)
+// Two CTA shapes from one template: BM = 128 (256 threads, the asymptotic shape) and BM = 64 (128 threads: twice the
+// tiles for products that cannot fill 148 SMs with 128 x 128 tiles -- 1024^3 is 64 of those).  BN = 128, BK = 16, 8x8 per
+// thread in both.
+constexpr int BN = 128, BK = 16;
+constexpr int LDT = 128 + 4;   // padded row of the k-major A tile and of the B tile (floats)
 constexpr int TILE = BK * LDT; // floats per operand per stage
 constexpr int STAGES = 2;
 constexpr size_t SMEM_BYTES = size_t(STAGES) * 2 * TILE * sizeof(float);
@@ -48,9 +51,10 @@ struct Frag {
     float4 a0, a1;            // A[k][ty*4..+3], A[k][64+ty*4..+3]
     ulonglong2 b0, b1;        // B[k][tx*4..+3] as two float2 pairs, B[k][64+tx*4..+3]
 };
+template <int HALF_M>
 __device__ __forceinline__ void load_frag(Frag &f, const float *ap, const float *bp, int kk) {
     f.a0 = *reinterpret_cast<const float4 *>(ap + kk * LDT);
-    f.a1 = *reinterpret_cast<const float4 *>(ap + kk * LDT + 64);
+    f.a1 = *reinterpret_cast<const float4 *>(ap + kk * LDT + HALF_M);
     f.b0 = *reinterpret_cast<const ulonglong2 *>(bp + kk * LDT);
     f.b1 = *reinterpret_cast<const ulonglong2 *>(bp + kk * LDT + 64);
 }
@@ -67,11 +71,12 @@ __device__ __forceinline__ void mma_frag(unsigned long long (&acc)[8][4], const 
     }
 }
 
-template <bool ALIGNED>
-__global__ void __launch_bounds__(THREADS, 2)
+template <bool ALIGNED, int BM>
+__global__ void __launch_bounds__(2 * BM, BM == 128 ? 2 : 4)
 sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, size_t lda,
                   const float *__restrict__ B, size_t ldb, float beta, float *__restrict__ C, size_t ldc,
                   int tiles_m, int tiles_n) {
+    constexpr int THREADS = 2 * BM, HALF_M = BM / 2;
     extern __shared__ __align__(16) float smem_f[];
     float *As = smem_f;                       // [STAGES][BK][LDT]  k-major
     float *Bs = smem_f + STAGES * TILE;       // [STAGES][BK][LDT]
@@ -86,15 +91,16 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     const int m0 = tm * BM, n0 = tn * BN;
 
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int tx = tid & 15, ty = tid >> 4;      // ty < BM / 8: rows ty*4.. and BM/2 + ty*4..
 
-    // global->shared copy roles.  A: thread owns k-quad (tid&3) of rows (tid>>2) and (tid>>2)+64.
+    // global->shared copy roles.  A: thread owns k-quad (tid&3) of rows (tid>>2) and (tid>>2)+BM/2.
     const int a_kq = (tid & 3) * 4, a_row = tid >> 2;
-    // B: thread owns float4 column chunk (tid&31) of k rows (tid>>5) and (tid>>5)+8.
+    // B: thread owns float4 column chunk (tid&31) of k rows (tid>>5) + i * THREADS/32.
+    constexpr int B_ROWS = THREADS / 32, B_PASSES = BK / B_ROWS;
     const int b_c4 = (tid & 31) * 4, b_row = tid >> 5;
-    const bool a_ok0 = m0 + a_row < M, a_ok1 = m0 + a_row + 64 < M;
+    const bool a_ok0 = m0 + a_row < M, a_ok1 = m0 + a_row + HALF_M < M;
     const float *a_src0 = A + size_t(a_ok0 ? m0 + a_row : 0) * lda + a_kq;
-    const float *a_src1 = A + size_t(a_ok1 ? m0 + a_row + 64 : 0) * lda + a_kq;
+    const float *a_src1 = A + size_t(a_ok1 ? m0 + a_row + HALF_M : 0) * lda + a_kq;
     const int b_gn = n0 + b_c4;
     const float *b_src = B + size_t(b_row) * ldb + (b_gn < N ? b_gn : 0);
     const int b_bytes_full = b_gn + 3 < N ? 16 : (b_gn < N ? (N - b_gn) * 4 : 0);
@@ -103,7 +109,7 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     // which execute on the same FMA pipe the FFMA2s need (ncu: ~15 per slab per warp, with pipe-throttle stalls).
     const float *pa0 = a_src0, *pa1 = a_src1;                 // slab being loaded: A columns k0 + a_kq ..
     const float *pb = b_src;                                  //                    B rows k0 + b_row (+8)
-    const size_t b_step = size_t(BK) * ldb, b_half = size_t(8) * ldb;
+    const size_t b_step = size_t(BK) * ldb, b_pass = size_t(B_ROWS) * ldb;
     auto load_a = [&](int k0, float4 &r0, float4 &r1) {
         r0 = make_float4(0.f, 0.f, 0.f, 0.f);
         r1 = r0;
@@ -125,19 +131,23 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
         pa0 += BK;
         pa1 += BK;
     };
+    // Transposing stores, conflict-free: k rows 8..15 keep their m index XOR 8 (a swizzle at the granularity of two
+    // float4 fragments, so the LDS.128 fragment loads below stay aligned and only pick one of two base pointers).  With
+    // the plain layout the four k-quads of a warp sat 16*kq banks apart -- quads 0/2 and 1/3 on the SAME banks: every
+    // STS.32 was a 2-way conflict (ncu r1: 136 M conflicts at n = 8192, shared-memory wavefronts at 67 % of peak).
     auto store_a = [&](float *as, const float4 &r0, const float4 &r1) {
-        float *p = as + a_kq * LDT + a_row;
+        float *p = as + a_kq * LDT + (a_row ^ (a_kq & 8));
         p[0] = r0.x; p[LDT] = r0.y; p[2 * LDT] = r0.z; p[3 * LDT] = r0.w;
-        p[64] = r1.x; p[LDT + 64] = r1.y; p[2 * LDT + 64] = r1.z; p[3 * LDT + 64] = r1.w;
+        p[HALF_M] = r1.x; p[LDT + HALF_M] = r1.y; p[2 * LDT + HALF_M] = r1.z; p[3 * LDT + HALF_M] = r1.w;
     };
     auto copy_b = [&](float *bs, int k0) {
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int row = b_row + 8 * i;
+        for (int i = 0; i < B_PASSES; ++i) {
+            const int row = b_row + B_ROWS * i;
             const bool ok = k0 + row < K;
             if (ALIGNED) {
                 const int bytes = ok ? b_bytes_full : 0;
-                cp_async16(smem_u32(bs + row * LDT + b_c4), bytes ? (i ? pb + b_half : pb) : B, bytes);
+                cp_async16(smem_u32(bs + row * LDT + b_c4), bytes ? pb + i * b_pass : B, bytes);
             } else {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
@@ -169,14 +179,15 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     for (int kt = 0; kt < KT; ++kt) {
         const int s = kt & 1;
         const float *ap = (s ? As + TILE : As) + ty * 4;
+        const float *ap8 = (s ? As + TILE : As) + ((ty * 4) ^ 8);     // k rows 8..15 (see store_a)
         const float *bp = (s ? Bs + TILE : Bs) + tx * 4;
         const bool more = kt + 1 < KT;
         float4 r0, r1;
         Frag f[2];
-        load_frag(f[0], ap, bp, 0);
+        load_frag<HALF_M>(f[0], ap, bp, 0);
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-            if (kk + 1 < BK) load_frag(f[(kk + 1) & 1], ap, bp, kk + 1);
+            if (kk + 1 < BK) load_frag<HALF_M>(f[(kk + 1) & 1], (kk + 1) & 8 ? ap8 : ap, bp, kk + 1);
             mma_frag(acc, f[kk & 1]);
             // slab kt+1 (A parked in registers, B by cp.async into the other stage) is requested AFTER the first k-step's
             // FFMA2s are in the pipe: right after the barrier every warp of the CTA would otherwise run ~100 address /
@@ -197,7 +208,7 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
     const bool vec_ok = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        const int row = m0 + ((i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        const int row = m0 + ((i < 4) ? ty * 4 + i : HALF_M + ty * 4 + (i - 4));
         if (row >= M) continue;
         float *crow = C + size_t(row) * ldc;
 #pragma unroll
@@ -230,34 +241,44 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st);
 
+template <bool ALIGNED, int BM>
+int sgemm_launch_cfg(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b, size_t ldb,
+                     float beta, float *c, size_t ldc, cudaStream_t st) {
+    static DeviceOnce attr_once;
+    const int tiles_m = int((m + BM - 1) / BM), tiles_n = int((n + BN - 1) / BN);
+    const size_t tiles = size_t(tiles_m) * tiles_n;
+    if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
+        RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<ALIGNED, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+        attr_once.done(od_);
+    }
+    sgemm_ffma_kernel<ALIGNED, BM><<<unsigned(tiles), 2 * BM, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb, beta, c,
+                                                                                ldc, tiles_m, tiles_n);
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+int g_sgemm_cfg = -1;    // rla_set_tuning("sgemm_cfg", v): -1 auto, 0 = 128 x 128 tiles, 1 = 64 x 128 tiles
+
 int sgemm_launch(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b,
                  size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
     if (m == 0 || n == 0) return RLA_OK;
     if (k == 0) return scale_c_launch<float>(m, n, beta, c, ldc, st);
     if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
-    static DeviceOnce attr_once[2];
     const bool aligned = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(b) & 15) == 0);
-    const int tiles_m = int((m + BM - 1) / BM), tiles_n = int((n + BN - 1) / BN);
-    const size_t tiles = size_t(tiles_m) * tiles_n;
-    if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
-    if (aligned) {
-        if (const int od_ = attr_once[1].pending(); od_ >= 0) {
-            RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-            attr_once[1].done(od_);
-        }
-        sgemm_ffma_kernel<true><<<unsigned(tiles), THREADS, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
-                                                                              beta, c, ldc, tiles_m, tiles_n);
-    } else {
-        if (const int od_ = attr_once[0].pending(); od_ >= 0) {
-            RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
-            attr_once[0].done(od_);
-        }
-        sgemm_ffma_kernel<false><<<unsigned(tiles), THREADS, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
-                                                                               beta, c, ldc, tiles_m, tiles_n);
+    // fewer 128 x 128 tiles than SMs: the 64 x 128 shape (twice the tiles) wins -- measured (tools/gemm_sweep.py s):
+    // 1024^3 33.2 vs 20.7 TFLOP/s, 512^3 7.0 vs 4.7; from 144 tiles (1536^3) on the big tile is ahead (49.2 vs 48.1)
+    int cfg = g_sgemm_cfg;
+    if (cfg < 0) {
+        const size_t t128 = ((m + 127) / 128) * ((n + 127) / 128);
+        cfg = t128 * 10 < size_t(device_num_sms()) * 9 ? 1 : 0;
     }
-    RLA_LAUNCHED();
-    return RLA_OK;
+    if (cfg == 1)
+        return aligned ? sgemm_launch_cfg<true, 64>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
+                       : sgemm_launch_cfg<false, 64>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    return aligned ? sgemm_launch_cfg<true, 128>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
+                   : sgemm_launch_cfg<false, 128>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
 }  // namespace rla
