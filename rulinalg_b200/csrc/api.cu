@@ -183,18 +183,24 @@ namespace {
 
 cudaStream_t pick_stream(void *s) { return static_cast<cudaStream_t>(s); }   // NULL = CUDA legacy default stream
 
-// Row-strided host matrix -> contiguous-ish device matrix (ld elements per row).
+// Row-strided host matrix -> contiguous-ish device matrix (ld elements per row).  Large pageable operands travel through
+// the calling thread's staging ring (host.cu); callers of download_matrix finish with cx.stager.finish().
+inline bool treat_as_pinned(const void *p, size_t bytes) {
+    return !g_host_stage || bytes < (size_t(2) << 20) || host_is_pinned(p);
+}
 template <typename T>
 int upload_matrix(T *dst, size_t ld, const T *src, size_t rs, size_t rows, size_t cols, cudaStream_t st) {
     if (rows == 0 || cols == 0) return RLA_OK;
-    RLA_CUDA(cudaMemcpy2DAsync(dst, ld * sizeof(T), src, rs * sizeof(T), cols * sizeof(T), rows, cudaMemcpyHostToDevice, st));
-    return RLA_OK;
+    Context &cx = thread_ctx();
+    return cx.stager.upload2d(dst, ld * sizeof(T), src, rs * sizeof(T), cols * sizeof(T), rows,
+                              treat_as_pinned(src, rows * cols * sizeof(T)), cx.device, st);
 }
 template <typename T>
 int download_matrix(T *dst, size_t rs, const T *src, size_t ld, size_t rows, size_t cols, cudaStream_t st) {
     if (rows == 0 || cols == 0) return RLA_OK;
-    RLA_CUDA(cudaMemcpy2DAsync(dst, rs * sizeof(T), src, ld * sizeof(T), cols * sizeof(T), rows, cudaMemcpyDeviceToHost, st));
-    return RLA_OK;
+    Context &cx = thread_ctx();
+    return cx.stager.download2d(dst, rs * sizeof(T), src, ld * sizeof(T), cols * sizeof(T), rows,
+                                treat_as_pinned(dst, rows * cols * sizeof(T)), cx.device, st);
 }
 
 // Host operand with arbitrary (possibly negative / non-unit) strides -> packed row-major copy.
@@ -521,7 +527,7 @@ int potrf_host(size_t n, T *a) {
     if (*hInfo != 0) return potrf_status(*hInfo);
     RLA_TRY(download_matrix(a, n, dA, ld, n, n, cx.stream));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
-    return RLA_OK;
+    return cx.stager.finish();
 }
 
 template <typename T>
@@ -574,7 +580,7 @@ int potri_host(size_t n, const T *l, T *inv) {
     if (*hInfo != 0) return RLA_ERR_SINGULAR;
     RLA_TRY(download_matrix(inv, n, dX, ld, n, n, cx.stream));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
-    return RLA_OK;
+    return cx.stager.finish();
 }
 
 template <typename T>
@@ -600,13 +606,18 @@ int getri_host(size_t n, const T *lu, const size_t *perm, T *inv) {
     if (*hInfo != 0) return RLA_ERR_SINGULAR;
     RLA_TRY(download_matrix(inv, n, dX, ld, n, n, cx.stream));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
-    return RLA_OK;
+    return cx.stager.finish();
 }
 
 }  // namespace
 
 void note_cuda_error(cudaError_t e) { tl_last_cuda = e; }
 void note_launch(unsigned n) { tl_launches += n; }
+uint64_t launch_count_take() {
+    const uint64_t v = tl_launches;
+    tl_launches = 0;
+    return v;
+}
 
 }  // namespace rla
 

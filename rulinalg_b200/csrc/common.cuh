@@ -14,6 +14,7 @@ namespace rla {
 // ---- per-thread error / launch accounting (api.cu) ---------------------------------------
 void note_cuda_error(cudaError_t e);
 void note_launch(unsigned n = 1);
+uint64_t launch_count_take();        // calling thread's launch count since its last take / reset (worker threads hand it to their parent)
 
 #define RLA_CUDA(expr)                                  \
     do {                                                \

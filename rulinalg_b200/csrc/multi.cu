@@ -15,6 +15,8 @@
 // the one-process-per-GPU driver (rulinalg_b200/sharded*.py, bench.py under torchrun) uses NCCL for the same step.
 #include <memory>
 #include <mutex>
+#include <thread>
+#include <vector>
 
 #include "context.cuh"
 
@@ -253,6 +255,10 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
             RLA_CUDA(cudaEventCreateWithFlags(&d.cx->lu_ws.ev_fact, cudaEventDisableTiming));
         }
         d.side = d.cx->lu_ws.side;
+        for (int which = 0; which < EV_COUNT; ++which) {       // all events exist before the worker threads start sharing them
+            cudaEvent_t e;
+            RLA_TRY(d.cx->event(size_t(which), &e));
+        }
     }
     auto evt = [&](int g, int which, cudaEvent_t *e) { return dv[g].cx->event(size_t(which), e); };
     auto info_ptr = [&](int g, int b) { return reinterpret_cast<int32_t *>(dv[g].buf[b] + info_off); };
@@ -319,33 +325,73 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         return Jn < nb ? lcol0(Jn) : dv[g].ncl;
     };
 
-    // block 0 has no predecessor
-    {
-        RLA_CUDA(cudaSetDevice(0));
-        RLA_TRY(factor_and_pack(0, 0, nullptr, dv[0].cx->stream));
-        cudaEvent_t packed;
-        RLA_TRY(evt(0, EV_PACKED0, &packed));
-        RLA_CUDA(cudaEventRecord(packed, dv[0].cx->stream));
-        for (int g = 1; g < G; ++g) {
-            RLA_CUDA(cudaSetDevice(g));
-            RLA_TRY(pull(g, 0, 0, packed));
+    // ---- the block loop, SPMD: one host thread per GPU issues that GPU's work (a single issuing thread costs ~160 API
+    //      calls per block at 8 GPUs and fell behind the devices: 353 ms where the same schedule takes 195 ms with one
+    //      process per GPU).  GPU-side ordering is by events as before; what the host threads must agree on is only
+    //      "the event I am about to wait on has already been recorded", which two monotonic sequence numbers give:
+    //        packed_seq       highest block whose [factored + packed] event has been recorded by its owner
+    //        pulled[g][b]     highest block of parity b whose arrival event GPU g has recorded (owners count as arrived)
+    std::atomic<int> packed_seq{-1}, failed{RLA_OK};
+    std::atomic<int> pulled[RLA_MAX_DEVICES][2];
+    for (int g = 0; g < G; ++g) pulled[g][0].store(-1), pulled[g][1].store(-1);
+    std::atomic<uint64_t> launches{0};
+    auto wait_for = [&](std::atomic<int> &x, int v) -> bool {
+        while (x.load(std::memory_order_acquire) < v) {
+            if (failed.load(std::memory_order_relaxed) != RLA_OK) return false;
+            std::this_thread::yield();
         }
-    }
-    for (int J = 0; J < nb; ++J) {
-        const int b = J & 1, owner = J % G;
-        const bool have_next = J + 1 < nb;
-        const int ow2 = (J + 1) % G;
-        const size_t w = width(J);
-        // ---- everyone: panel J has arrived -> interchanges on the local columns outside the block ----
-        for (int g = 0; g < G; ++g) {
-            RLA_CUDA(cudaSetDevice(g));
-            cudaStream_t st = dv[g].cx->stream;
+        return true;
+    };
+    auto worker = [&](int g) -> int {
+        RLA_CUDA(cudaSetDevice(g));
+        cudaStream_t st = dv[g].cx->stream;
+        auto panel_event = [&](int b, cudaEvent_t *e) { return evt(g, b ? EV_PANEL1 : EV_PANEL0, e); };
+        auto do_pull = [&](int J) -> int {
+            const int b = J & 1, owner = J % G;
+            if (!wait_for(packed_seq, J)) return RLA_ERR_CUDA;
+            cudaEvent_t packed;
+            RLA_TRY(evt(owner, b ? EV_PACKED1 : EV_PACKED0, &packed));
+            RLA_TRY(pull(g, J, b, packed));
+            pulled[g][b].store(J, std::memory_order_release);
+            return RLA_OK;
+        };
+        auto do_factor = [&](int J, const int32_t *prev_info, cudaStream_t fs) -> int {
+            const int b = J & 1;
+            if (J >= 2) {
+                // buf[b] and the [packed] event of parity b are about to be reused: every GPU must have issued its waits on /
+                // pulls of block J-2 (and, where they read THIS GPU's buffer, the pulls must have completed)
+                for (int o = 0; o < G; ++o) {
+                    if (o == g) continue;
+                    if (!wait_for(pulled[o][b], J - 2)) return RLA_ERR_CUDA;
+                    if ((J - 2) % G == g) {
+                        cudaEvent_t got;
+                        RLA_TRY(evt(o, b ? EV_PANEL1 : EV_PANEL0, &got));
+                        RLA_CUDA(cudaStreamWaitEvent(fs, got, 0));
+                    }
+                }
+            }
+            RLA_TRY(factor_and_pack(J, b, prev_info, fs));
+            cudaEvent_t packed;
+            RLA_TRY(evt(g, b ? EV_PACKED1 : EV_PACKED0, &packed));
+            RLA_CUDA(cudaEventRecord(packed, fs));
+            pulled[g][b].store(J, std::memory_order_release);
+            packed_seq.store(J, std::memory_order_release);
+            return RLA_OK;
+        };
+        // block 0 has no predecessor
+        if (g == 0) RLA_TRY(do_factor(0, nullptr, st)); else RLA_TRY(do_pull(0));
+        for (int J = 0; J < nb; ++J) {
+            const int b = J & 1, owner = J % G;
+            const bool have_next = J + 1 < nb;
+            const int ow2 = (J + 1) % G;
+            const size_t w = width(J);
+            // ---- panel J has arrived -> interchanges on the local columns outside the block ----
             if (g != owner) {
                 cudaEvent_t got;
-                RLA_TRY(evt(g, b ? EV_PANEL1 : EV_PANEL0, &got));
+                RLA_TRY(panel_event(b, &got));
                 RLA_CUDA(cudaStreamWaitEvent(st, got, 0));
             } else if (J > 0) {
-                cudaEvent_t packed;                       // factored on the owner's side stream
+                cudaEvent_t packed;                       // factored on my side stream
                 RLA_TRY(evt(g, b ? EV_PACKED1 : EV_PACKED0, &packed));
                 RLA_CUDA(cudaStreamWaitEvent(st, packed, 0));
             }
@@ -356,39 +402,37 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
             } else {
                 RLA_TRY(lu_laswp_dev<T>(A(g), dv[g].ld, int(w), dv[g].buf[b], info_ptr(g, b), 0, int(dv[g].ncl), 0, 0, st));
             }
-        }
-        // ---- the next block's owner: head update, then factor + pack on its side stream ----
-        cudaEvent_t packed_next = nullptr;
-        if (have_next) {
-            LuDev &o = dv[ow2];
-            RLA_CUDA(cudaSetDevice(ow2));
-            const size_t lo = first_after(ow2, J), wn = width(J + 1);      // lo = block J+1's first local column
-            RLA_TRY(update(ow2, J, b, lo, lo + wn));
-            cudaEvent_t head;
-            RLA_TRY(evt(ow2, EV_HEAD, &head));
-            RLA_CUDA(cudaEventRecord(head, o.cx->stream));
-            RLA_CUDA(cudaStreamWaitEvent(o.side, head, 0));                // also orders buf[1-b] after its local readers
-            for (int g = 0; g < G; ++g) {                                   // ... and after the GPUs that pulled panel J-1 from it
-                if (g == ow2 || J == 0 || (J - 1) % G != ow2) continue;
-                cudaEvent_t got;
-                RLA_TRY(evt(g, (1 - b) ? EV_PANEL1 : EV_PANEL0, &got));
-                RLA_CUDA(cudaStreamWaitEvent(o.side, got, 0));
-            }
-            RLA_TRY(factor_and_pack(J + 1, 1 - b, info_ptr(ow2, b), o.side));
-            RLA_TRY(evt(ow2, (1 - b) ? EV_PACKED1 : EV_PACKED0, &packed_next));
-            RLA_CUDA(cudaEventRecord(packed_next, o.side));
-        }
-        // ---- everyone: (the rest of) the update with panel J; the pulls of panel J+1 hide under it ----
-        for (int g = 0; g < G; ++g) {
-            RLA_CUDA(cudaSetDevice(g));
             const size_t lo = first_after(g, J);
             if (have_next && g == ow2) {
-                RLA_TRY(update(g, J, b, lo + width(J + 1), dv[g].ncl));
+                // ---- the next block's owner: its columns first, then factor + pack on the side stream under the tail update ----
+                const size_t wn = width(J + 1);               // lo = block J+1's first local column
+                RLA_TRY(update(g, J, b, lo, lo + wn));
+                cudaEvent_t head;
+                RLA_TRY(evt(g, EV_HEAD, &head));
+                RLA_CUDA(cudaEventRecord(head, st));
+                RLA_CUDA(cudaStreamWaitEvent(dv[g].side, head, 0));    // also orders buf[1-b] after its local readers
+                RLA_TRY(do_factor(J + 1, info_ptr(g, b), dv[g].side));
+                RLA_TRY(update(g, J, b, lo + wn, dv[g].ncl));
             } else {
-                if (have_next) RLA_TRY(pull(g, J + 1, 1 - b, packed_next));
+                if (have_next) RLA_TRY(do_pull(J + 1));          // the pull of panel J+1 hides under the update
                 RLA_TRY(update(g, J, b, lo, dv[g].ncl));
             }
         }
+        launches.fetch_add(launch_count_take(), std::memory_order_relaxed);
+        return RLA_OK;
+    };
+    {
+        std::vector<std::thread> threads;
+        for (int g = 1; g < G; ++g)
+            threads.emplace_back([&, g] {
+                const int st = worker(g);
+                if (st != RLA_OK) failed.store(st, std::memory_order_relaxed);
+            });
+        const int st0 = worker(0);
+        if (st0 != RLA_OK) failed.store(st0, std::memory_order_relaxed);
+        for (auto &t : threads) t.join();
+        note_launch(unsigned(launches.load()));
+        if (failed.load() != RLA_OK) return failed.load();
     }
     // ---- perm, info, download ----
     const int lastb = (nb - 1) & 1;
