@@ -766,3 +766,81 @@ def test_launch_counter_and_version(rla):
     _ = rla.Matrix.ones(4, 4) * rla.Matrix.ones(4, 4)
     assert l.rla_launch_count() >= 1
     assert b"sm_100a" in l.rla_version()
+
+
+# ============================================================================ parity holes named by the round-1 review
+def _freivalds_and_samples(rla, oracle, dtype, m, k, n, samples=1024):
+    """C = A B on device-generated U[0,1) operands at a size the CPU oracle cannot sweep: Freivalds C x vs A (B x) through
+    the library's gemv (a different, HBM-bound kernel) within 6 gamma_k |A||B||x|, plus sampled entries against
+    extended-precision dots within the Higham bound gamma_k sum|a||b| and 8 sqrt(k) u relative."""
+    import torch
+    l = rla.lib()
+    s = torch.cuda.current_stream().cuda_stream
+    f64 = np.dtype(dtype) == np.float64
+    tdt = torch.float64 if f64 else torch.float32
+    fill = l.rla_fill_uniform_f64_dev if f64 else l.rla_fill_uniform_f32_dev
+    gemm = l.rla_dgemm_dev if f64 else l.rla_sgemm_dev
+    gemv = l.rla_dgemv_dev if f64 else l.rla_sgemv_dev
+    a = torch.empty(m, k, dtype=tdt, device="cuda"); b = torch.empty(k, n, dtype=tdt, device="cuda")
+    c = torch.full((m, n), float("nan"), dtype=tdt, device="cuda")
+    assert fill(a.data_ptr(), m, k, k, 12, 0, 0.0, 1.0, s) == 0
+    assert fill(b.data_ptr(), k, n, n, 2049, 0, 0.0, 1.0, s) == 0
+    assert rla.check(gemm(m, k, n, 1.0, a.data_ptr(), k, b.data_ptr(), n, 0.0, c.data_ptr(), n, s)) == 0
+    x = torch.empty(n, dtype=tdt, device="cuda")
+    assert fill(x.data_ptr(), 1, n, n, 4000, 0, 0.0, 1.0, s) == 0
+    y = torch.empty(k, dtype=tdt, device="cuda"); z = torch.empty(m, dtype=tdt, device="cuda"); w = torch.empty(m, dtype=tdt, device="cuda")
+    assert rla.check(gemv(k, n, b.data_ptr(), n, x.data_ptr(), y.data_ptr(), s)) == 0
+    assert rla.check(gemv(m, k, a.data_ptr(), k, y.data_ptr(), z.data_ptr(), s)) == 0
+    assert rla.check(gemv(m, n, c.data_ptr(), n, x.data_ptr(), w.data_ptr(), s)) == 0
+    torch.cuda.synchronize()
+    g = gamma(max(k, n), dtype)
+    assert bool(torch.all((w.double() - z.double()).abs() <= 6 * g * z.double().abs()))
+    rng = np.random.default_rng(7)
+    ii = rng.integers(0, m, samples); jj = rng.integers(0, n, samples)
+    it, jt = torch.as_tensor(ii, device="cuda"), torch.as_tensor(jj, device="cuda")
+    a_rows = a.index_select(0, it).cpu().numpy()
+    b_cols = b.index_select(1, jt).t().contiguous().cpu().numpy()
+    got = c[it, jt].double().cpu().numpy()
+    idx = np.arange(samples)
+    truth, absd = oracle.gemm_truth_samples(a_rows, b_cols.T, idx, idx)
+    err = np.abs(got - truth)
+    assert np.all(err <= gamma(k, dtype) * absd)
+    assert np.max(err / np.abs(truth)) < 8 * math.sqrt(k) * U(dtype)
+
+
+def test_gemm_f32_8192_freivalds_and_samples(rla, oracle):
+    _freivalds_and_samples(rla, oracle, np.float32, 8192, 8192, 8192)
+
+
+def test_gemm_f64_16384_freivalds_and_samples(rla, oracle):
+    _freivalds_and_samples(rla, oracle, np.float64, 16384, 16384, 16384)
+
+
+def test_gemm_f32_small_tile_shape_vs_oracle(rla, oracle):
+    """the 64 x 128 SGEMM shape (products with fewer 128 x 128 tiles than SMs) against the oracle, incl. ragged edges"""
+    for (m, k, n) in ((1024, 1024, 1024), (1000, 515, 777), (70, 33, 130)):
+        a = oracle.fill_uniform((m, k), 12, np.float32)
+        b = oracle.fill_uniform((k, n), 2049, np.float32)
+        assert rla.lib().rla_set_tuning(b"sgemm_cfg", 1) == 0
+        try:
+            c = gpu_gemm_dev(rla, a, b)
+        finally:
+            rla.lib().rla_set_tuning(b"sgemm_cfg", -1)
+        oracle.assert_matrix_eq(c, oracle.gemm(a, b), comp="ulp", tol=int(math.ceil(4 * math.sqrt(k))))
+
+
+def test_lu_4096_pivot_sequence_matches_oracle(rla, oracle):
+    """BASELINE config C3 (n = 4096): SURVEY 8d promises the reference's pivot sequence at this size (the oracle's
+    unblocked elimination takes ~15 s on one host core), the reconstruction gate of the smaller sizes and solve parity."""
+    n = 4096
+    a = oracle.fill_uniform((n, n), 12)
+    ref = oracle.lu_decompose(a, fast=True)
+    f = decompose(rla, a)
+    lu_checks(rla, oracle, a, f, ref)            # asserts the identical pivot sequence + |P^-1 L U - A| <= 8 n u rho max|A|
+    b = np.ones(n)
+    x = f.solve(rla.Vector(b)).data()
+    x_ref = oracle.lu_solve(ref[0], ref[1], b, fast=True)
+    eps = np.finfo(np.float64).eps
+    assert np.max(np.abs(a @ x - b)) / (np.max(np.sum(np.abs(a), axis=1)) * np.max(np.abs(x)) * n * eps) <= 16
+    kappa = np.linalg.cond(a, 1)
+    assert np.max(np.abs(x - x_ref)) / np.max(np.abs(x_ref)) <= 8 * n * U(np.float64) * kappa
