@@ -197,6 +197,11 @@ RLA_API int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *
  *                  U12 = L11^-1 A12 and A22 -= L21 U12 on local columns [c0,c1)
  *   rowid_*      : the row-origin vector every rank carries; perm_from_rowid gives PartialPivLu.p.perm */
 RLA_API size_t rla_lu_plan_bytes(void);
+/* Largest n rla_?getrf / rla_?getrf_dev accept on the current device (a 64-column panel of n rows must fit the shared
+ * memory of the panel kernel's row CTAs): 57 771 for f64, 115 542 for f32 on a 148-SM B200.  Larger n returns
+ * RLA_ERR_INVALID before anything is enqueued (the reference has no limit; an n = 57 771 f64 matrix is 26.7 GB).
+ * 0 when no device is usable. */
+RLA_API size_t rla_lu_max_n(size_t elem_size);
 /* development aid: with rla_set_tuning("lu_dbg", 8) the four inner panels of the last outer block record 64 x 8 words
  * each (globaltimer stamps in slots 0..6, the pivot row in slot 7); copies 4 x 512 words to host2048 */
 RLA_API int rla_debug_lu_trace(unsigned long long *host2048);

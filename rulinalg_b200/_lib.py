@@ -27,7 +27,7 @@ SYMBOLS = [
     "rla_host_free_pinned", "rla_memcpy_h2d", "rla_memcpy_d2h", "rla_stream_sync",
     "rla_dgemm_dev", "rla_sgemm_dev", "rla_dgetrf_dev", "rla_sgetrf_dev", "rla_dgetrs_dev", "rla_sgetrs_dev",
     "rla_fill_uniform_f64_dev", "rla_fill_uniform_f32_dev",
-    "rla_lu_plan_bytes", "rla_debug_lu_trace", "rla_debug_divcheck", "rla_dlu_factor_block_dev", "rla_dlu_laswp_dev", "rla_dlu_update_dev",
+    "rla_lu_plan_bytes", "rla_lu_max_n", "rla_debug_lu_trace", "rla_debug_divcheck", "rla_dlu_factor_block_dev", "rla_dlu_laswp_dev", "rla_dlu_update_dev",
     "rla_lu_rowid_init_dev", "rla_lu_rowid_apply_dev", "rla_lu_perm_from_rowid_dev",
     "rla_measure_peak", "rla_set_tuning", "rla_strerror", "rla_last_cuda_error", "rla_version", "rla_launch_count", "rla_launch_count_reset",
 ]
@@ -98,6 +98,8 @@ def lib():
     l.rla_fill_uniform_f64_dev.argtypes = [P, sz, sz, sz, u64, u64, dbl, dbl, P]
     l.rla_fill_uniform_f32_dev.argtypes = [P, sz, sz, sz, u64, u64, flt, flt, P]
     l.rla_lu_plan_bytes.restype = sz
+    l.rla_lu_max_n.argtypes = [sz]
+    l.rla_lu_max_n.restype = sz
     l.rla_debug_lu_trace.argtypes = [P]
     l.rla_debug_divcheck.argtypes = [i32, i32, u64, u64, C.POINTER(u64)]
     l.rla_dlu_factor_block_dev.argtypes = [sz, P, sz, sz, sz, sz, P, P, P]

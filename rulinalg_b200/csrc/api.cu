@@ -805,6 +805,10 @@ int rla_sgetrs_dev(size_t n, const float *lu, size_t ld, const int64_t *d_perm, 
                                static_cast<int32_t *>(cx.dSync.p), pick_stream(stream));
 }
 size_t rla_lu_plan_bytes(void) { return lu_plan_bytes(); }
+size_t rla_lu_max_n(size_t elem_size) {
+    if (ensure_ctx() != RLA_OK || (elem_size != 4 && elem_size != 8)) return 0;
+    return lu_max_n(elem_size);
+}
 int rla_debug_lu_trace(unsigned long long *host512) { return lu_trace_fetch(host512); }
 int rla_debug_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count, unsigned long long *mismatches) {
     if (!mismatches) return RLA_ERR_INVALID;

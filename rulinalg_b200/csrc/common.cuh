@@ -109,6 +109,7 @@ int potri_launch(size_t n, const T *l, size_t ld, T *x, size_t ldx, T *m, int64_
 template <typename T>
 int gemv_launch(size_t m, size_t n, const T *a, size_t lda, const T *x, T *y, cudaStream_t st);
 size_t lu_plan_bytes();
+size_t lu_max_n(size_t elem_size);
 int lu_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count, unsigned long long *mismatches);
 int lu_trace_fetch(unsigned long long *host512);
 template <typename T>

@@ -1833,6 +1833,13 @@ void lu_workspace_release(LuWorkspace &ws) {
 
 size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
 
+// Largest n the panel kernels take: a 64-column panel of n rows must fit the shared memory of (SMs - 1) row CTAs at
+// 200 KB each (57 771 rows in f64, 115 542 in f32 on a 148-SM B200; an n = 57 771 f64 matrix is 26.7 GB).
+size_t lu_max_n(size_t elem_size) {
+    const size_t rows_per_cta = (size_t(200) * 1024) / (size_t(PLDS) * elem_size);
+    return rows_per_cta * size_t(device_num_sms() - 1);
+}
+
 // development / test aid: div_via_rcp against the IEEE division over `count` pseudo-random operand pairs
 int lu_divcheck(int f32, int mode, unsigned long long seed, unsigned long long count, unsigned long long *mismatches) {
     unsigned long long *d = nullptr;
@@ -1856,7 +1863,7 @@ int lu_trace_fetch(unsigned long long *host512) {
 template <typename T>
 int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st,
                  const LuRowsFinal *rows_final) {
-    if (n_ > 0x7fffffffull / 2) return RLA_ERR_INVALID;
+    if (n_ > lu_max_n(sizeof(T))) return RLA_ERR_INVALID;      // checked up front: nothing has been enqueued yet
     const int n = int(n_);
     RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
     if (n == 0) return RLA_OK;

@@ -223,7 +223,7 @@ template <typename T>
 int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
     std::lock_guard<std::mutex> lk(g_multi_mu);
     DeviceRestore restore;
-    if (n_ > 0x3fffffffull) return RLA_ERR_INVALID;
+    if (n_ > 0x3fffffffull || n_ > lu_max_n(sizeof(T))) return RLA_ERR_INVALID;
     const int n = int(n_);
     const int nb = int((n_ + LU_BLOCK - 1) / LU_BLOCK);
     const int G = multi_device_count() < nb ? multi_device_count() : nb;

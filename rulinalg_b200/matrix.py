@@ -330,13 +330,18 @@ class LUP:
 class PartialPivLu:
     """rulinalg::matrix::decomposition::PartialPivLu<T> over librla_b200 (lu.rs:130-300)."""
 
+    # factors of at most this many bytes also stay resident in HBM for repeated solves (rla_dgetrf_keep); larger ones are
+    # re-uploaded by solve() -- an object that pins gigabytes of HBM until Python's GC runs is a bad default.  release() /
+    # the context-manager protocol return the device copy early.
+    KEEP_RESIDENT_BYTES = 512 << 20
+
     def __init__(self, lu: Matrix, p: PermutationMatrix, handle=None):
         self.lu = lu
         self.p = p
         self._handle = handle        # device-resident copy of the factors for repeated solves (f64)
 
     @staticmethod
-    def decompose(matrix: Matrix) -> "PartialPivLu":
+    def decompose(matrix: Matrix, keep_resident: bool | None = None) -> "PartialPivLu":
         n = matrix.cols()
         if matrix.rows() != n:
             raise Panic("Matrix must be square for LU decomposition.")
@@ -344,15 +349,28 @@ class PartialPivLu:
         pre = _dtype_pre(lu._arr.dtype)
         perm = np.zeros(n, dtype=np.uintp)
         handle = None
-        if pre == "d":
+        if keep_resident is None:
+            keep_resident = n * n * 8 <= PartialPivLu.KEEP_RESIDENT_BYTES
+        if pre == "d" and keep_resident:
             h = C.c_void_p()
             st = _lib.lib().rla_dgetrf_keep(n, lu.as_ptr(), perm.ctypes.data, C.byref(h))
             handle = h
         else:
-            st = _lib.lib().rla_sgetrf(n, lu.as_ptr(), perm.ctypes.data)
+            st = getattr(_lib.lib(), f"rla_{pre}getrf")(n, lu.as_ptr(), perm.ctypes.data)
         if _lib.check(st) == _lib.RLA_ERR_SINGULAR:
             raise Error(ErrorKind.DivByZero, _LU_ILL_MSG)
         return PartialPivLu(lu, PermutationMatrix(perm), handle)
+
+    def release(self) -> None:
+        """Return the device-resident copy of the factors (solve() then re-uploads `lu` / `p`)."""
+        self.__del__()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.release()
+        return False
 
     def __del__(self):
         h = getattr(self, "_handle", None)

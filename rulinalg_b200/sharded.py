@@ -100,6 +100,9 @@ class RowPanelGemm:
                 self._gemm(p.m_local, p.k, p.n, 1.0, a_local.data_ptr(), a_local.stride(0), b.data_ptr(), b.stride(0),
                            0.0, c_local.data_ptr(), c_local.stride(0), sptr)
                 return
+            if not p.k_chunks:                            # k == 0: the reference yields zeros (empty sum)
+                c_local.zero_()
+                return
             comm = self._comm_stream
             comm.wait_stream(stream)                      # B on rank 0 was produced on the compute stream
             with torch.cuda.stream(comm):
@@ -116,6 +119,8 @@ class RowPanelGemm:
         # CPU tensors: plumbing-only path for the gloo tests (gemm_fn must be injected)
         if self._gemm is None:
             raise RuntimeError("RowPanelGemm on CPU tensors needs an injected gemm_fn; the product path is CUDA-only")
+        if not p.k_chunks:
+            c_local.zero_()
         for j, (k0, kc) in enumerate(p.k_chunks):
             if p.world_size > 1:
                 chunk = b[k0:k0 + kc]

@@ -10,7 +10,9 @@ fn main() {
     let out = PathBuf::from(env::var("OUT_DIR").unwrap());
     let csrc = PathBuf::from(env::var("RLA_B200_CSRC").unwrap_or_else(|_| "rla_b200/csrc".into()));
     let cuda = env::var("CUDA_HOME").unwrap_or_else(|_| "/usr/local/cuda".into());
-    let srcs = ["api.cu", "dgemm.cu", "sgemm.cu", "lu.cu", "solve.cu", "fill.cu", "gemv.cu"];
+    // every source rulinalg_b200/csrc/Makefile builds (tests/test_abi.py keeps the two lists identical)
+    let srcs = ["api.cu", "host.cu", "multi.cu", "dgemm.cu", "sgemm.cu", "lu.cu", "solve.cu", "fill.cu", "gemv.cu",
+                "cholesky.cu", "peak.cu"];
     let mut objs = Vec::new();
     for s in srcs.iter() {
         let obj = out.join(format!("{}.o", s));
@@ -34,4 +36,10 @@ fn main() {
     println!("cargo:rustc-link-lib=static=rla_b200");
     println!("cargo:rustc-link-lib=dylib=cudart");
     println!("cargo:rustc-link-lib=dylib=stdc++");
+    println!("cargo:rustc-link-lib=dylib=pthread");   // staging pool / drainer / per-GPU issue threads (host.cu, multi.cu)
+    // no NCCL: inside one process the multi-GPU exchange is peer memory (multi.cu); NCCL is only used by the
+    // one-process-per-GPU Python driver (rulinalg_b200/sharded*.py)
+    for h in ["common.cuh", "context.cuh"].iter() {
+        println!("cargo:rerun-if-changed={}", csrc.join(h).display());
+    }
 }

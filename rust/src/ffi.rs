@@ -45,6 +45,23 @@ extern "C" {
     pub fn rla_dpotri(n: usize, l: *const f64, inv: *mut f64) -> i32;
     pub fn rla_spotri(n: usize, l: *const f32, inv: *mut f32) -> i32;
     pub fn rla_strerror(status: i32) -> *const ::std::os::raw::c_char;
+    /// One host process, N GPUs: after `rla_set_devices(n)` large `rla_dgemm` / `rla_sgemm` / `rla_dgetrf` calls shard over
+    /// GPUs 0..n-1 (row panels + peer-memory fan-out of B; 1D block-cyclic LU).  Results are bit-identical to n = 1.
+    pub fn rla_set_devices(n_gpus: i32) -> i32;
+    pub fn rla_get_devices() -> i32;
+    pub fn rla_device_count() -> i32;
+    /// Returns the calling thread's streams / buffers / staging rings and the multi-GPU contexts (also runs at thread exit).
+    pub fn rla_shutdown() -> i32;
+}
+
+/// Opt-in for multi-GPU boxes, e.g. from the embedding application's start-up:
+/// `ffi::use_gpus(8)` -> every later `&a * &b` / `PartialPivLu::decompose` large enough to profit is sharded.
+pub fn use_gpus(n: i32) {
+    let st = unsafe { rla_set_devices(n) };
+    if st != RLA_OK {
+        let msg = unsafe { ::std::ffi::CStr::from_ptr(rla_strerror(st)) };
+        panic!("librla_b200: rla_set_devices({}) -> {} ({})", n, st, msg.to_string_lossy())
+    }
 }
 
 /// Cholesky::decompose statuses (cholesky.rs:151-158): both are ErrorKind::DecompFailure.

@@ -117,3 +117,31 @@ def test_host_mirror_logic_cpu(rla):
     assert rla.Matrix(2, 2, [2., 3., 1., 2.]).det() == 1.0
     assert rla.Matrix(3, 3, [1., 2., 3., 4., 5., 6., 7., 8., 9.]).det() == 0.0
     assert rla.Matrix(3, 3, [2., 0., 0., 0., 3., 0., 0., 0., 4.]).det() == 24.0
+
+
+def test_rust_shim_lists_every_source_and_symbol():
+    """rust/build.rs must compile exactly the sources the Makefile builds (round 1 shipped a build.rs without
+    cholesky.cu: undefined symbols at link), and rust/src/ffi.rs may only name symbols the header declares."""
+    mk = open(os.path.join(ROOT, "rulinalg_b200", "csrc", "Makefile")).read()
+    mk_srcs = sorted(re.search(r"^SRCS\s*=\s*(.+)$", mk, re.M).group(1).split())
+    on_disk = sorted(f for f in os.listdir(os.path.join(ROOT, "rulinalg_b200", "csrc")) if f.endswith(".cu"))
+    assert mk_srcs == on_disk
+    rs = open(os.path.join(ROOT, "rust", "build.rs")).read()
+    rs_srcs = sorted(re.findall(r'"(\w+\.cu)"', rs))
+    assert rs_srcs == mk_srcs, (rs_srcs, mk_srcs)
+    ffi = open(os.path.join(ROOT, "rust", "src", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (rla_\w+)\s*\(", ffi))
+    assert bound and bound <= set(header_symbols()), bound - set(header_symbols())
+    for must in ("rla_dgemm", "rla_sgemm", "rla_dgetrf", "rla_dgetrs", "rla_set_devices", "rla_shutdown"):
+        assert must in bound
+
+
+def test_multi_device_entry_points_fail_loudly_without_gpu(rla):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CPU-box check")
+    l = rla.lib()
+    assert l.rla_device_count() == 0
+    assert l.rla_set_devices(2) == rla._lib.RLA_ERR_NO_DEVICE if hasattr(rla, "_lib") else l.rla_set_devices(2) == -3
+    assert l.rla_get_devices() == 1
+    assert l.rla_shutdown() == 0

@@ -844,3 +844,15 @@ def test_lu_4096_pivot_sequence_matches_oracle(rla, oracle):
     assert np.max(np.abs(a @ x - b)) / (np.max(np.sum(np.abs(a), axis=1)) * np.max(np.abs(x)) * n * eps) <= 16
     kappa = np.linalg.cond(a, 1)
     assert np.max(np.abs(x - x_ref)) / np.max(np.abs(x_ref)) <= 8 * n * U(np.float64) * kappa
+
+
+def test_lu_size_limit_is_reported_up_front(rla):
+    """panels taller than the row CTAs' shared memory are refused BEFORE anything is enqueued, with the limit
+    queryable (rla_lu_max_n)."""
+    l = rla.lib()
+    nmax = int(l.rla_lu_max_n(8))
+    assert 50000 < nmax < 70000 and int(l.rla_lu_max_n(4)) == 2 * nmax
+    buf = rla.DeviceBuffer(1024)
+    assert l.rla_dgetrf_dev(nmax + 1, buf.ptr, nmax + 1, buf.ptr, buf.ptr, None) == 2      # RLA_ERR_INVALID, nothing touched
+    assert l.rla_stream_sync(None) == 0
+    buf.free()
