@@ -10,7 +10,10 @@ present) and the pivot search needs no communication.  Per column block:
               A22 -= L21 U12 on the local blocks right of J (DMMA kernel)
 
 With look-ahead the owner of block J+1 updates and factors that block first and its broadcast runs on a
-side stream while everybody finishes the tail update of block J.
+side stream while everybody finishes the tail update of block J.  The factored panel J+1 is on the critical
+path of exactly ONE other rank -- the owner of block J+2, which needs it for its own head update -- so with more
+than two ranks it goes there first as a point-to-point send (67 MB at NVLink rate instead of an 8-rank
+broadcast), and the broadcast to everybody else follows off the critical path.
 
 torch.distributed is plumbing (rendezvous + the broadcast); all arithmetic is librla_b200's CUDA.  The layout
 arithmetic is pure host logic and is what the gloo CPU test covers.
@@ -103,6 +106,11 @@ class BlockCyclicLu:
         self.plan_bytes = plan_bytes
         nbuf = 2 if self.lookahead else 1
         self.bufs = [torch.empty(HEADER_BYTES + n * layout.block * 8, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
+        # the next-next owner receives the panel twice (point-to-point first, then as a member of the broadcast): the second
+        # copy lands in a scratch buffer so it never overwrites bytes its head update may be reading
+        self.p2p_first = self.lookahead and layout.world_size > 2
+        self.scratch = torch.empty_like(self.bufs[0]) if self.p2p_first else None
+        self.comm2 = torch.cuda.Stream() if self.p2p_first else None     # carries the redundant broadcast copy only
         self.rowid = torch.empty(n, dtype=torch.int32, device=dev)
         self.perm = torch.empty(n, dtype=torch.int64, device=dev)
         self.info = torch.zeros(1, dtype=torch.int32, device=dev)
@@ -133,15 +141,35 @@ class BlockCyclicLu:
             panel = buf[HEADER_BYTES:HEADER_BYTES + rows * w * 8].view(torch.float64).view(rows, w)
             panel.copy_(a_loc[row0:, lc0:lc0 + w])
 
-    def _broadcast(self, J, buf, stream):
+    def _broadcast(self, J, buf, stream, first_to=None):
+        """panel J from its owner to everybody; with `first_to` (a rank) that rank gets it point-to-point first and takes
+        the broadcast copy into the scratch buffer.  Returns an event recorded when THIS rank's copy in `buf` is usable."""
         import torch
         import torch.distributed as dist
         lay = self.layout
         if lay.world_size == 1:
-            return
+            return None
         rows, w = lay.n - J * lay.block, lay.width(J)
+        nbytes = HEADER_BYTES + rows * w * 8
+        owner = lay.owner(J)
+        ev = torch.cuda.Event()
         with torch.cuda.stream(stream):
-            dist.broadcast(buf[:HEADER_BYTES + rows * w * 8], src=lay.owner(J), group=self.group)
+            if first_to is not None and first_to != owner:
+                if lay.rank == owner:
+                    dist.send(buf[:nbytes], dst=first_to, group=self.group)
+                    dist.broadcast(buf[:nbytes], src=owner, group=self.group)
+                elif lay.rank == first_to:
+                    dist.recv(buf[:nbytes], src=owner, group=self.group)
+                    ev.record(stream)                                   # usable here: before the broadcast has even started
+                    with torch.cuda.stream(self.comm2):                 # (its own stream: `stream` factors the next block next)
+                        dist.broadcast(self.scratch[:nbytes], src=owner, group=self.group)
+                    return ev
+                else:
+                    dist.broadcast(buf[:nbytes], src=owner, group=self.group)
+            else:
+                dist.broadcast(buf[:nbytes], src=owner, group=self.group)
+            ev.record(stream)
+        return ev
 
     def _swaps(self, a_loc, J, buf, stream):
         """everyone: block J's row interchanges on the row-origin vector and on the local columns outside it"""
@@ -191,7 +219,7 @@ class BlockCyclicLu:
                 self.info.copy_(self._info_view(buf))
         else:
             side = self.side
-            ev_ready, ev_head, ev_next = self.ev[0], self.ev[1], self.ev[2]
+            ev_ready, ev_head = self.ev[0], self.ev[1]
             # block 0 has no predecessor: factor + broadcast on the main stream
             if lay.rank == lay.owner(0):
                 self._factor_and_pack(a_loc, 0, self.bufs[0], self.info, main)
@@ -200,6 +228,8 @@ class BlockCyclicLu:
                 cur, nxt = self.bufs[J % 2], self.bufs[(J + 1) % 2]
                 have_next = J + 1 < nb
                 lo = lay.first_local_col_after(J)
+                # panel J+1 is urgent for the owner of block J+2 only
+                first = lay.owner(J + 2) if (self.p2p_first and J + 2 < nb) else None
                 self._swaps(a_loc, J, cur, main)
                 if have_next and lay.rank == lay.owner(J + 1):
                     wn = lay.width(J + 1)                          # lo is block J+1's first local column
@@ -207,18 +237,17 @@ class BlockCyclicLu:
                     ev_head.record(main)
                     side.wait_event(ev_head)                       # also orders `nxt` after its last readers
                     self._factor_and_pack(a_loc, J + 1, nxt, self._info_view(cur), side)
-                    self._broadcast(J + 1, nxt, side)
-                    ev_next.record(side)
+                    ev_next = self._broadcast(J + 1, nxt, side, first)
                     self._update(a_loc, J, cur, main, lo + wn, ncl)                 # tail, overlapped
                 else:
+                    ev_next = None
                     if have_next:
                         ev_ready.record(main)                      # everything that read `nxt` (panel J-1) is queued
                         side.wait_event(ev_ready)
-                        self._broadcast(J + 1, nxt, side)          # receive panel J+1 under the update below
-                        ev_next.record(side)
+                        ev_next = self._broadcast(J + 1, nxt, side, first)   # receive panel J+1 under the update below
                     self._update(a_loc, J, cur, main, lo, ncl)
                 self.info.copy_(self._info_view(cur))
-                if have_next:
+                if ev_next is not None:
                     main.wait_event(ev_next)
         self._check(self._l.rla_lu_perm_from_rowid_dev(self.rowid.data_ptr(), self.perm.data_ptr(), lay.n,
                                                        self.info.data_ptr(), main.cuda_stream))

@@ -116,17 +116,18 @@ def _nccl_worker(rank, world, port, n, lookahead, out_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,lookahead", [(700, False), (1280, True), (2048, True)])
-def test_block_cyclic_lu_world2_nccl(tmp_path, oracle, n, lookahead):
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs two GPUs")
-    world = 2
+@pytest.mark.parametrize("world,n,lookahead", [(2, 700, False), (2, 1280, True), (2, 2048, True),
+                                               (4, 2048, True), (4, 3000, True), (8, 4608, True)])
+def test_block_cyclic_lu_world2_nccl(tmp_path, oracle, world, n, lookahead):
+    """world > 2 also exercises the point-to-point-first path (the next-next owner gets the panel before the broadcast)"""
+    if torch.cuda.device_count() < world:
+        pytest.skip(f"needs {world} GPUs")
     mp.spawn(_nccl_worker, args=(world, _free_port(), n, lookahead, str(tmp_path)), nprocs=world, join=True)
     lay = BlockCyclicLayout(n, world, 0)
     got = gather_columns([np.load(tmp_path / f"lu{r}.npy") for r in range(world)], lay)
     perms = [np.load(tmp_path / f"perm{r}.npy") for r in range(world)]
     assert all(int(np.load(tmp_path / f"info{r}.npy")[0]) == 0 for r in range(world))
-    assert np.array_equal(perms[0], perms[1])
+    assert all(np.array_equal(perms[0], q) for q in perms[1:])
     a = oracle.fill_uniform((n, n), 12)
     ref_lu, ref_perm = _single_gpu_lu(a)
     assert perms[0].tolist() == ref_perm.tolist()
