@@ -198,7 +198,7 @@ RLA_API int rla_sgetri_dev(size_t n, const float *lu, size_t ld, const int64_t *
  *   rowid_*      : the row-origin vector every rank carries; perm_from_rowid gives PartialPivLu.p.perm */
 RLA_API size_t rla_lu_plan_bytes(void);
 /* Largest n rla_?getrf / rla_?getrf_dev accept on the current device (a 64-column panel of n rows must fit the shared
- * memory of the panel kernel's row CTAs): 57 771 for f64, 115 542 for f32 on a 148-SM B200.  Larger n returns
+ * memory of the panel kernel's row CTAs): 57 771 for f64, 115 689 for f32 on a 148-SM B200.  Larger n returns
  * RLA_ERR_INVALID before anything is enqueued (the reference has no limit; an n = 57 771 f64 matrix is 26.7 GB).
  * 0 when no device is usable. */
 RLA_API size_t rla_lu_max_n(size_t elem_size);

@@ -85,7 +85,7 @@ void Context::destroy() {
         stager.release();
         for (cudaEvent_t e : events) cudaEventDestroy(e);
         events.clear();
-        for (Buffer *b : {&dA, &dB, &dC, &dPerm, &dInfo, &dVec, &dVec2, &dSync, &dTrsv, &dChol, &dPanel[0], &dPanel[1], &dRowid, &hSmall})
+        for (Buffer *b : {&dA, &dB, &dC, &dPerm, &dInfo, &dVec, &dVec2, &dSync, &dTrsv, &dChol, &dPanel[0], &dPanel[1], &dRowid, &hSmall, &hPack, &dPack})
             b->release();
         lu_workspace_release(lu_ws);
     }
@@ -211,6 +211,44 @@ void pack_host(std::vector<T> &out, const T *src, ptrdiff_t rs, ptrdiff_t cs, si
         for (size_t j = 0; j < cols; ++j) out[i * cols + j] = src[ptrdiff_t(i) * rs + ptrdiff_t(j) * cs];
 }
 
+// Small calls (the only shapes the reference itself benchmarks: benches/linalg/matrix.rs:40-65, lu.rs:52-139) are bound by
+// API calls, not by bytes: the general path costs ~45 us in three pageable copies, events and three stream syncs.  Here
+// the operands are packed into ONE pinned block by the CPU (nanoseconds at these sizes), travel in ONE H2D copy, and the
+// result comes back in ONE D2H copy behind a single synchronisation: 2 copies + the launches + 1 sync.
+constexpr size_t SMALL_CALL_BYTES = size_t(256) << 10;
+inline size_t round16(size_t b) { return (b + 15) / 16 * 16; }
+
+template <typename T>
+int gemm_host_small(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, ptrdiff_t csa, const T *b,
+                    ptrdiff_t rsb, ptrdiff_t csb, T beta, T *c, ptrdiff_t rsc, ptrdiff_t csc) {
+    Context &cx = thread_ctx();
+    const size_t lda = pad_ld(k ? k : 1, sizeof(T)), ldb = pad_ld(n, sizeof(T)), ldc = pad_ld(n, sizeof(T));
+    const size_t offA = 0, offB = round16(m * lda * sizeof(T)), offC = offB + round16((k ? k : 1) * ldb * sizeof(T));
+    const size_t total = offC + round16(m * ldc * sizeof(T));
+    RLA_TRY(cx.hPack.ensure(total));
+    RLA_TRY(cx.dPack.ensure(total));
+    unsigned char *hp = static_cast<unsigned char *>(cx.hPack.p), *dp = static_cast<unsigned char *>(cx.dPack.p);
+    T *ha = reinterpret_cast<T *>(hp + offA), *hb = reinterpret_cast<T *>(hp + offB), *hc = reinterpret_cast<T *>(hp + offC);
+    for (size_t i = 0; i < m; ++i)
+        for (size_t j = 0; j < k; ++j) ha[i * lda + j] = a[ptrdiff_t(i) * rsa + ptrdiff_t(j) * csa];
+    for (size_t i = 0; i < k; ++i)
+        for (size_t j = 0; j < n; ++j) hb[i * ldb + j] = b[ptrdiff_t(i) * rsb + ptrdiff_t(j) * csb];
+    size_t up = offC;
+    if (beta != T(0)) {
+        for (size_t i = 0; i < m; ++i)
+            for (size_t j = 0; j < n; ++j) hc[i * ldc + j] = c[ptrdiff_t(i) * rsc + ptrdiff_t(j) * csc];
+        up = total;
+    }
+    RLA_CUDA(cudaMemcpyAsync(dp, hp, up, cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(gemm_dev<T>(m, k, n, alpha, reinterpret_cast<T *>(dp + offA), lda, reinterpret_cast<T *>(dp + offB), ldb, beta,
+                        reinterpret_cast<T *>(dp + offC), ldc, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hc, dp + offC, m * ldc * sizeof(T), cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    for (size_t i = 0; i < m; ++i)
+        for (size_t j = 0; j < n; ++j) c[ptrdiff_t(i) * rsc + ptrdiff_t(j) * csc] = hc[i * ldc + j];
+    return RLA_OK;
+}
+
 // The host-pointer GEMM.  Pipeline: B is uploaded whole (it is reused by every row panel); A is
 // uploaded and C downloaded in row panels so PCIe transfers overlap the kernel of the previous /
 // next panel (three streams, events).
@@ -221,6 +259,8 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
     if ((k > 0 && (!a || !b)) || !c) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
     Context &cx = thread_ctx();
+    if ((m * k + k * n + m * n) * sizeof(T) <= SMALL_CALL_BYTES)
+        return gemm_host_small<T>(m, k, n, alpha, a, rsa, csa, b, rsb, csb, beta, c, rsc, csc);
 
     std::vector<T> pa, pb, pc;
     const T *ha = a, *hb = b;
@@ -349,6 +389,54 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
     return RLA_OK;
 }
 
+// Small-call twins of decompose / solve (see gemm_host_small): device block = [info 16 B | perm n*8 | lu n*ld (| b n)].
+template <typename T>
+int getrf_host_small(size_t n, T *lu, size_t *perm) {
+    Context &cx = thread_ctx();
+    const size_t ld = pad_ld(n, sizeof(T));
+    const size_t offP = 16, offA = offP + round16(n * sizeof(int64_t)), total = offA + round16(n * ld * sizeof(T));
+    RLA_TRY(cx.hPack.ensure(total));
+    RLA_TRY(cx.dPack.ensure(total));
+    unsigned char *hp = static_cast<unsigned char *>(cx.hPack.p), *dp = static_cast<unsigned char *>(cx.dPack.p);
+    T *ha = reinterpret_cast<T *>(hp + offA);
+    for (size_t i = 0; i < n; ++i) memcpy(ha + i * ld, lu + i * n, n * sizeof(T));
+    RLA_CUDA(cudaMemcpyAsync(dp + offA, hp + offA, n * ld * sizeof(T), cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(getrf_launch<T>(n, reinterpret_cast<T *>(dp + offA), ld, reinterpret_cast<int64_t *>(dp + offP),
+                            reinterpret_cast<int32_t *>(dp), cx.lu_ws, cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hp, dp, total, cudaMemcpyDeviceToHost, cx.stream));
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*reinterpret_cast<int32_t *>(hp) != 0) return RLA_ERR_SINGULAR;
+    memcpy(perm, hp + offP, n * sizeof(int64_t));
+    for (size_t i = 0; i < n; ++i) memcpy(lu + i * n, ha + i * ld, n * sizeof(T));
+    return RLA_OK;
+}
+
+template <typename T>
+int getrs_host_small(size_t n, const T *lu, const size_t *perm, T *b) {
+    Context &cx = thread_ctx();
+    const size_t ld = pad_ld(n, sizeof(T));
+    const size_t offB = 16, offP = offB + round16(n * sizeof(T)), offA = offP + round16(n * sizeof(int64_t));
+    const size_t total = offA + round16(n * ld * sizeof(T));
+    RLA_TRY(cx.hPack.ensure(total));
+    RLA_TRY(cx.dPack.ensure(total));
+    RLA_TRY(cx.dTrsv.ensure(3 * n * sizeof(T)));
+    RLA_TRY(cx.dSync.ensure(64));
+    unsigned char *hp = static_cast<unsigned char *>(cx.hPack.p), *dp = static_cast<unsigned char *>(cx.dPack.p);
+    T *ha = reinterpret_cast<T *>(hp + offA);
+    memcpy(hp + offB, b, n * sizeof(T));
+    memcpy(hp + offP, perm, n * sizeof(int64_t));
+    for (size_t i = 0; i < n; ++i) memcpy(ha + i * ld, lu + i * n, n * sizeof(T));
+    RLA_CUDA(cudaMemcpyAsync(dp + offB, hp + offB, total - offB, cudaMemcpyHostToDevice, cx.stream));
+    RLA_TRY(getrs_launch<T>(n, reinterpret_cast<const T *>(dp + offA), ld, reinterpret_cast<const int64_t *>(dp + offP),
+                            reinterpret_cast<T *>(dp + offB), static_cast<T *>(cx.dTrsv.p), reinterpret_cast<int32_t *>(dp),
+                            static_cast<int32_t *>(cx.dSync.p), cx.stream));
+    RLA_CUDA(cudaMemcpyAsync(hp, dp, offP, cudaMemcpyDeviceToHost, cx.stream));          // [info | x]
+    RLA_CUDA(cudaStreamSynchronize(cx.stream));
+    if (*reinterpret_cast<int32_t *>(hp) != 0) return RLA_ERR_SINGULAR;                   // b left untouched
+    memcpy(b, hp + offB, n * sizeof(T));
+    return RLA_OK;
+}
+
 // PartialPivLu::decompose through host memory (lu.rs:163-195 consumes a Vec): upload, factor, and download every block
 // row as soon as it can no longer change (getrf_launch's rows_final hook), so the D2H of the factors runs under the
 // factorisation of the rest instead of after it.  Pageable memory travels through the staging ring.
@@ -360,6 +448,7 @@ int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm,
     Context &cx = thread_ctx();
     if (!keep_dev && multi_device_count() > 1 && n >= 8192)      // rla_set_devices(N): 1D block-cyclic over N GPUs (multi.cu)
         return getrf_host_multi<T>(n, lu, perm, cx.stager);
+    if (!keep_dev && n * n * sizeof(T) <= SMALL_CALL_BYTES) return getrf_host_small<T>(n, lu, perm);
     const size_t ld = pad_ld(n, sizeof(T));
     T *dA;
     int64_t *dP;
@@ -449,6 +538,7 @@ int getrs_host(size_t n, const T *lu, const size_t *perm, T *b) {
     if (!lu || !perm || !b) return RLA_ERR_INVALID;
     RLA_TRY(ensure_ctx());
     Context &cx = thread_ctx();
+    if (n * n * sizeof(T) <= SMALL_CALL_BYTES) return getrs_host_small<T>(n, lu, perm, b);
     const size_t ld = pad_ld(n, sizeof(T));
     RLA_TRY(cx.dA.ensure(n * ld * sizeof(T)));
     RLA_TRY(cx.dPerm.ensure(n * sizeof(int64_t)));

@@ -79,10 +79,11 @@ struct Context {
     cudaStream_t p2p = nullptr;          // peer pulls (multi-device paths)
     Buffer dA, dB, dC, dPerm, dInfo, dVec, dVec2, dSync, dTrsv, dChol, dPanel[2], dRowid;
     Buffer hSmall;                       // pinned scalars (info, perm)
+    Buffer hPack, dPack;                 // small-call fast path: operands packed into ONE pinned block <-> one device block
     LuWorkspace lu_ws;
     Stager stager;                       // pinned ring for pageable host operands (allocated on first use)
     std::vector<cudaEvent_t> events;
-    Context() { hSmall.pinned_host = true; }
+    Context() { hSmall.pinned_host = true; hPack.pinned_host = true; }
     ~Context() { destroy(); }
     Context(const Context &) = delete;
     Context &operator=(const Context &) = delete;

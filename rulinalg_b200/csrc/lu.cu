@@ -1834,7 +1834,7 @@ void lu_workspace_release(LuWorkspace &ws) {
 size_t lu_plan_bytes() { return sizeof(LaswpPlan); }
 
 // Largest n the panel kernels take: a 64-column panel of n rows must fit the shared memory of (SMs - 1) row CTAs at
-// 200 KB each (57 771 rows in f64, 115 542 in f32 on a 148-SM B200; an n = 57 771 f64 matrix is 26.7 GB).
+// 200 KB each (57 771 rows in f64, 115 689 in f32 on a 148-SM B200; an n = 57 771 f64 matrix is 26.7 GB).
 size_t lu_max_n(size_t elem_size) {
     const size_t rows_per_cta = (size_t(200) * 1024) / (size_t(PLDS) * elem_size);
     return rows_per_cta * size_t(device_num_sms() - 1);

@@ -851,7 +851,7 @@ def test_lu_size_limit_is_reported_up_front(rla):
     queryable (rla_lu_max_n)."""
     l = rla.lib()
     nmax = int(l.rla_lu_max_n(8))
-    assert 50000 < nmax < 70000 and int(l.rla_lu_max_n(4)) == 2 * nmax
+    assert 50000 < nmax < 70000 and 2 * nmax <= int(l.rla_lu_max_n(4)) < 2 * nmax + 300
     buf = rla.DeviceBuffer(1024)
     assert l.rla_dgetrf_dev(nmax + 1, buf.ptr, nmax + 1, buf.ptr, buf.ptr, None) == 2      # RLA_ERR_INVALID, nothing touched
     assert l.rla_stream_sync(None) == 0
