@@ -41,6 +41,16 @@ inline int check(int st) {
     if (st == RLA_OK || st == RLA_ERR_SINGULAR || st == RLA_ERR_NOT_POSITIVE) return st;
     throw RlaFailure(st);
 }
+}  // namespace detail
+
+// Multi-GPU opt-in (rla_set_devices): from here on `a * b` and `PartialPivLu<T>::decompose` shard large problems over
+// GPUs 0..n-1 of the box from this one process (row panels / 1D block-cyclic, peer-memory exchange); results are
+// bit-identical to one GPU.  use_gpus(1) restores single-GPU behaviour; shutdown() returns every library resource.
+inline void use_gpus(int n) { detail::check(rla_set_devices(n)); }
+inline int gpus_in_use() { return rla_get_devices(); }
+inline void shutdown() { detail::check(rla_shutdown()); }
+
+namespace detail {
 template <typename T> struct Abi;
 template <> struct Abi<double> {
     static int gemm(size_t m, size_t k, size_t n, const double *a, ptrdiff_t rsa, const double *b, ptrdiff_t rsb, double *c) {

@@ -13,6 +13,9 @@
 //
 // There is no NCCL in this file: inside one process the exchange is peer memory (cudaMemcpyPeer semantics under UVA);
 // the one-process-per-GPU driver (rulinalg_b200/sharded*.py, bench.py under torchrun) uses NCCL for the same step.
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <memory>
 #include <mutex>
 #include <thread>
@@ -234,8 +237,14 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
     auto width = [&](int J) { return size_t(J) * LU_BLOCK + LU_BLOCK <= n_ ? LU_BLOCK : n_ - size_t(J) * LU_BLOCK; };
     auto lcol0 = [&](int J) { return size_t(J / G) * LU_BLOCK; };
 
+    // RLA_MULTI_TRACE=1: phase times on stderr (the phases are hard dependencies anyway, so the extra syncs cost nothing)
+    const bool trace = getenv("RLA_MULTI_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto ms_since = [&](std::chrono::steady_clock::time_point t) {
+        return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t).count();
+    };
     LuDev dv[RLA_MAX_DEVICES];
-    enum { EV_UP = 0, EV_HEAD, EV_READY, EV_PACKED0, EV_PACKED1, EV_PANEL0, EV_PANEL1, EV_DONE, EV_COUNT };
+    enum { EV_UP = 0, EV_HEAD, EV_READY, EV_DONE, EV_COUNT };      // + per block J: [arrived] EV_COUNT + 2J, [packed] EV_COUNT + 2J + 1
     for (int g = 0; g < G; ++g) {
         LuDev &d = dv[g];
         RLA_TRY(device_ctx(g, &d.cx));
@@ -255,7 +264,7 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
             RLA_CUDA(cudaEventCreateWithFlags(&d.cx->lu_ws.ev_fact, cudaEventDisableTiming));
         }
         d.side = d.cx->lu_ws.side;
-        for (int which = 0; which < EV_COUNT; ++which) {       // all events exist before the worker threads start sharing them
+        for (int which = 0; which < EV_COUNT + 2 * nb; ++which) {   // all events exist before the worker threads start sharing them
             cudaEvent_t e;
             RLA_TRY(d.cx->event(size_t(which), &e));
         }
@@ -279,6 +288,11 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         RLA_CUDA(cudaEventRecord(e, dv[g].cx->copy_in));
         RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->stream, e, 0));
     }
+    double t_up = 0, t_fact = 0;
+    if (trace) {
+        for (int g = 0; g < G; ++g) { RLA_CUDA(cudaSetDevice(g)); RLA_CUDA(cudaStreamSynchronize(dv[g].cx->copy_in)); }
+        t_up = ms_since(t_begin);
+    }
     // row-origin vector (-> perm) lives on GPU 0
     RLA_CUDA(cudaSetDevice(0));
     RLA_TRY(dv[0].cx->dRowid.ensure(n_ * sizeof(int32_t)));
@@ -299,21 +313,6 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
                                    n_ - row0, cudaMemcpyDeviceToDevice, st));
         return RLA_OK;
     };
-    // receiver side: pull panel J from its owner's buf[b] once `packed` has fired; `ready` orders the pull after this
-    // GPU's last readers of its own buf[b]
-    auto pull = [&](int g, int J, int b, cudaEvent_t packed) -> int {
-        const int owner = J % G;
-        const size_t bytes = LU_HEADER + (n_ - size_t(J) * LU_BLOCK) * width(J) * sizeof(T);
-        cudaEvent_t ready, got;
-        RLA_TRY(evt(g, EV_READY, &ready));
-        RLA_CUDA(cudaEventRecord(ready, dv[g].cx->stream));
-        RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->p2p, ready, 0));
-        RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->p2p, packed, 0));
-        RLA_CUDA(cudaMemcpyPeerAsync(dv[g].buf[b], g, dv[owner].buf[b], owner, bytes, dv[g].cx->p2p));
-        RLA_TRY(evt(g, b ? EV_PANEL1 : EV_PANEL0, &got));
-        RLA_CUDA(cudaEventRecord(got, dv[g].cx->p2p));
-        return RLA_OK;
-    };
     auto update = [&](int g, int J, int b, size_t c0, size_t c1) -> int {
         if (c1 <= c0) return RLA_OK;
         return lu_update_dev<T>(n, A(g), dv[g].ld, int(size_t(J) * LU_BLOCK), int(width(J)), panel_ptr(g, b), width(J), int(c0), int(c1),
@@ -325,15 +324,22 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         return Jn < nb ? lcol0(Jn) : dv[g].ncl;
     };
 
-    // ---- the block loop, SPMD: one host thread per GPU issues that GPU's work (a single issuing thread costs ~160 API
-    //      calls per block at 8 GPUs and fell behind the devices: 353 ms where the same schedule takes 195 ms with one
-    //      process per GPU).  GPU-side ordering is by events as before; what the host threads must agree on is only
-    //      "the event I am about to wait on has already been recorded", which two monotonic sequence numbers give:
-    //        packed_seq       highest block whose [factored + packed] event has been recorded by its owner
-    //        pulled[g][b]     highest block of parity b whose arrival event GPU g has recorded (owners count as arrived)
+    // ---- the block loop, SPMD: one host thread per GPU issues that GPU's work.  GPU-side ordering is by events (one
+    //      [packed] and one [arrived] event per block and GPU, never re-recorded); what the host threads must agree on is
+    //      only "the event I am about to wait on has already been recorded", which two monotonic sequence numbers give:
+    //        packed_seq    highest block whose [factored + packed] event has been recorded by its owner
+    //        pulled[g]     highest block whose [arrived] event GPU g has recorded (owners count as arrived)
+    //      Fan-out of panel J: it is on the critical path of exactly ONE GPU, the owner of block J+1, which therefore pulls
+    //      first and alone (full NVLink rate: 67 MB in ~0.1 ms); the others follow down a binary tree (each holder serves
+    //      its two children one after the other), ~4 transfer times in all at 8 GPUs.  The first version let all N-1 GPUs
+    //      pull from the owner at once: 7 x 67 MB through one GPU's egress put ~0.7 ms on EVERY block's critical path
+    //      (8 GPUs, n = 32768: 357 ms against the NCCL driver's 195 ms).
+    // finished block rows stream back to a pinned host matrix during the factorisation when the block-cyclic layout is
+    // regular (n a multiple of 256 * G: each GPU's share of a row is nblk chunks of 2 KiB at a constant host stride)
+    const bool stream_rows = pinned && n_ % (LU_BLOCK * size_t(G)) == 0;
     std::atomic<int> packed_seq{-1}, failed{RLA_OK};
-    std::atomic<int> pulled[RLA_MAX_DEVICES][2];
-    for (int g = 0; g < G; ++g) pulled[g][0].store(-1), pulled[g][1].store(-1);
+    std::atomic<int> pulled[RLA_MAX_DEVICES];
+    for (int g = 0; g < G; ++g) pulled[g].store(-1);
     std::atomic<uint64_t> launches{0};
     auto wait_for = [&](std::atomic<int> &x, int v) -> bool {
         while (x.load(std::memory_order_acquire) < v) {
@@ -342,39 +348,72 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         }
         return true;
     };
+    auto got_event = [&](int dev, int J, cudaEvent_t *e) { return evt(dev, EV_COUNT + 2 * J, e); };
+    auto packed_event = [&](int dev, int J, cudaEvent_t *e) { return evt(dev, EV_COUNT + 2 * J + 1, e); };
     auto worker = [&](int g) -> int {
         RLA_CUDA(cudaSetDevice(g));
         cudaStream_t st = dv[g].cx->stream;
-        auto panel_event = [&](int b, cudaEvent_t *e) { return evt(g, b ? EV_PANEL1 : EV_PANEL0, e); };
+        // buf[J & 1] of this GPU is about to be overwritten with block J: whoever read block J-2 out of it (its children in
+        // that block's tree) must be done.  Conservative and cheap: wait for every receiver's [arrived] event of block J-2.
+        auto buffer_reusable = [&](int J, cudaStream_t on) -> int {
+            if (J < 2) return RLA_OK;
+            for (int o = 0; o < G; ++o) {
+                if (o == g || o == (J - 2) % G) continue;           // (owners do not pull)
+                if (!wait_for(pulled[o], J - 2)) return RLA_ERR_CUDA;
+                cudaEvent_t got;
+                RLA_TRY(got_event(o, J - 2, &got));
+                RLA_CUDA(cudaStreamWaitEvent(on, got, 0));
+            }
+            return RLA_OK;
+        };
         auto do_pull = [&](int J) -> int {
-            const int b = J & 1, owner = J % G;
-            if (!wait_for(packed_seq, J)) return RLA_ERR_CUDA;
-            cudaEvent_t packed;
-            RLA_TRY(evt(owner, b ? EV_PACKED1 : EV_PACKED0, &packed));
-            RLA_TRY(pull(g, J, b, packed));
-            pulled[g][b].store(J, std::memory_order_release);
+            const int b = J & 1, O = J % G, P = (J + 1) % G;
+            // tree: node 0 = owner, node 1 = the next block's owner, then the other GPUs in ascending order
+            int node = 0, order[RLA_MAX_DEVICES];
+            order[0] = O;
+            int cnt = 1;
+            if (P != O) order[cnt++] = P;
+            for (int x = 0; x < G; ++x)
+                if (x != O && x != P) order[cnt++] = x;
+            for (int i = 0; i < cnt; ++i)
+                if (order[i] == g) node = i;
+            const int parent = (node - 1) / 2, src = order[parent];
+            cudaStream_t ps = dv[g].cx->p2p;
+            RLA_TRY(buffer_reusable(J, ps));
+            cudaEvent_t e;
+            if (parent == 0) {
+                if (!wait_for(packed_seq, J)) return RLA_ERR_CUDA;
+                RLA_TRY(packed_event(O, J, &e));
+            } else {
+                if (!wait_for(pulled[src], J)) return RLA_ERR_CUDA;
+                RLA_TRY(got_event(src, J, &e));
+            }
+            RLA_CUDA(cudaStreamWaitEvent(ps, e, 0));
+            if ((node & 1) == 0) {                                  // second child: after its sibling, so each gets the full link
+                const int sib = order[node - 1];
+                if (!wait_for(pulled[sib], J)) return RLA_ERR_CUDA;
+                RLA_TRY(got_event(sib, J, &e));
+                RLA_CUDA(cudaStreamWaitEvent(ps, e, 0));
+            }
+            const size_t bytes = LU_HEADER + (n_ - size_t(J) * LU_BLOCK) * width(J) * sizeof(T);
+            cudaEvent_t ready, got;
+            RLA_TRY(evt(g, EV_READY, &ready));                      // my own readers of buf[b] (update J-2) are queued on `st`
+            RLA_CUDA(cudaEventRecord(ready, st));
+            RLA_CUDA(cudaStreamWaitEvent(ps, ready, 0));
+            RLA_CUDA(cudaMemcpyPeerAsync(dv[g].buf[b], g, dv[src].buf[b], src, bytes, ps));
+            RLA_TRY(got_event(g, J, &got));
+            RLA_CUDA(cudaEventRecord(got, ps));
+            pulled[g].store(J, std::memory_order_release);
             return RLA_OK;
         };
         auto do_factor = [&](int J, const int32_t *prev_info, cudaStream_t fs) -> int {
             const int b = J & 1;
-            if (J >= 2) {
-                // buf[b] and the [packed] event of parity b are about to be reused: every GPU must have issued its waits on /
-                // pulls of block J-2 (and, where they read THIS GPU's buffer, the pulls must have completed)
-                for (int o = 0; o < G; ++o) {
-                    if (o == g) continue;
-                    if (!wait_for(pulled[o][b], J - 2)) return RLA_ERR_CUDA;
-                    if ((J - 2) % G == g) {
-                        cudaEvent_t got;
-                        RLA_TRY(evt(o, b ? EV_PANEL1 : EV_PANEL0, &got));
-                        RLA_CUDA(cudaStreamWaitEvent(fs, got, 0));
-                    }
-                }
-            }
+            RLA_TRY(buffer_reusable(J, fs));
             RLA_TRY(factor_and_pack(J, b, prev_info, fs));
             cudaEvent_t packed;
-            RLA_TRY(evt(g, b ? EV_PACKED1 : EV_PACKED0, &packed));
+            RLA_TRY(packed_event(g, J, &packed));
             RLA_CUDA(cudaEventRecord(packed, fs));
-            pulled[g][b].store(J, std::memory_order_release);
+            pulled[g].store(J, std::memory_order_release);
             packed_seq.store(J, std::memory_order_release);
             return RLA_OK;
         };
@@ -388,11 +427,11 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
             // ---- panel J has arrived -> interchanges on the local columns outside the block ----
             if (g != owner) {
                 cudaEvent_t got;
-                RLA_TRY(panel_event(b, &got));
+                RLA_TRY(got_event(g, J, &got));
                 RLA_CUDA(cudaStreamWaitEvent(st, got, 0));
             } else if (J > 0) {
                 cudaEvent_t packed;                       // factored on my side stream
-                RLA_TRY(evt(g, b ? EV_PACKED1 : EV_PACKED0, &packed));
+                RLA_TRY(packed_event(g, J, &packed));
                 RLA_CUDA(cudaStreamWaitEvent(st, packed, 0));
             }
             if (g == 0) RLA_TRY(lu_rowid_apply_dev(dv[g].buf[b], rowid, info_ptr(g, b), st));
@@ -417,6 +456,22 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
                 if (have_next) RLA_TRY(do_pull(J + 1));          // the pull of panel J+1 hides under the update
                 RLA_TRY(update(g, J, b, lo, dv[g].ncl));
             }
+            if (stream_rows) {
+                // rows [J*256, J*256 + w) of every local column are final from here on (later interchanges only touch rows
+                // below): ONE strided 3-D copy takes this GPU's 256-column chunks of those rows to their places in the host
+                // matrix while the factorisation goes on
+                cudaEvent_t e;
+                RLA_TRY(evt(g, EV_DONE, &e));
+                RLA_CUDA(cudaEventRecord(e, st));
+                RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->copy_out, e, 0));
+                const size_t chunk = LU_BLOCK * sizeof(T), nblk = dv[g].ncl / LU_BLOCK, row0 = size_t(J) * LU_BLOCK;
+                cudaMemcpy3DParms p3 = {};
+                p3.srcPtr = make_cudaPitchedPtr(A(g) + row0 * dv[g].ld, chunk, chunk, nblk);
+                p3.dstPtr = make_cudaPitchedPtr(lu + row0 * n_ + size_t(g) * LU_BLOCK, size_t(G) * chunk, chunk, nblk);
+                p3.extent = make_cudaExtent(chunk, nblk, w);
+                p3.kind = cudaMemcpyDeviceToHost;
+                RLA_CUDA(cudaMemcpy3DAsync(&p3, dv[g].cx->copy_out));
+            }
         }
         launches.fetch_add(launch_count_take(), std::memory_order_relaxed);
         return RLA_OK;
@@ -433,6 +488,15 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         for (auto &t : threads) t.join();
         note_launch(unsigned(launches.load()));
         if (failed.load() != RLA_OK) return failed.load();
+    }
+    if (trace) {
+        for (int g = 0; g < G; ++g) {
+            RLA_CUDA(cudaSetDevice(g));
+            RLA_CUDA(cudaStreamSynchronize(dv[g].cx->stream));
+            RLA_CUDA(cudaStreamSynchronize(dv[g].side));
+            RLA_CUDA(cudaStreamSynchronize(dv[g].cx->p2p));
+        }
+        t_fact = ms_since(t_begin);
     }
     // ---- perm, info, download ----
     const int lastb = (nb - 1) & 1;
@@ -453,7 +517,7 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         RLA_CUDA(cudaEventRecord(done, dv[g].cx->stream));
         RLA_CUDA(cudaStreamWaitEvent(dv[g].cx->copy_out, done, 0));
     }
-    for (int J = 0; J < nb; ++J) {
+    for (int J = 0; J < nb && !stream_rows; ++J) {
         const int g = J % G;
         RLA_CUDA(cudaSetDevice(g));
         RLA_TRY(stg.download2d(lu + size_t(J) * LU_BLOCK, n_ * sizeof(T), A(g) + lcol0(J), dv[g].ld * sizeof(T), width(J) * sizeof(T), n_,
@@ -467,6 +531,9 @@ int getrf_host_multi(size_t n_, T *lu, size_t *perm, Stager &stg) {
         RLA_CUDA(cudaStreamSynchronize(dv[g].cx->p2p));
     }
     RLA_TRY(stg.finish());
+    if (trace)
+        fprintf(stderr, "[rla multi getrf] n=%d gpus=%d pinned=%d: upload %.1f ms, factor %.1f ms, download %.1f ms, total %.1f ms\n", n, G,
+                int(pinned), t_up, t_fact - t_up, ms_since(t_begin) - t_fact, ms_since(t_begin));
     return *static_cast<int32_t *>(dv[0].cx->hSmall.p) != 0 ? RLA_ERR_SINGULAR : RLA_OK;
 }
 

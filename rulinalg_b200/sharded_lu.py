@@ -10,10 +10,13 @@ present) and the pivot search needs no communication.  Per column block:
               A22 -= L21 U12 on the local blocks right of J (DMMA kernel)
 
 With look-ahead the owner of block J+1 updates and factors that block first and its broadcast runs on a
-side stream while everybody finishes the tail update of block J.  The factored panel J+1 is on the critical
-path of exactly ONE other rank -- the owner of block J+2, which needs it for its own head update -- so with more
-than two ranks it goes there first as a point-to-point send (67 MB at NVLink rate instead of an 8-rank
-broadcast), and the broadcast to everybody else follows off the critical path.
+side stream while everybody finishes the tail update of block J.
+
+Measured and switched off (`p2p_first=True` re-enables it): the factored panel J+1 is on the critical path of exactly
+ONE other rank -- the owner of block J+2 -- so it can go there first as a point-to-point send, the broadcast to
+everybody else following off the critical path.  Through torch.distributed this is SLOWER (8 GPUs, n = 32768:
+234.7 ms vs 195.3 ms): ProcessGroupNCCL serialises unbatched send/recv with every other operation of the group, so
+the extra 67 MB transfer lands in front of the broadcast instead of beside it.
 
 torch.distributed is plumbing (rendezvous + the broadcast); all arithmetic is librla_b200's CUDA.  The layout
 arithmetic is pure host logic and is what the gloo CPU test covers.
@@ -91,7 +94,7 @@ def gather_columns(locals_, layout: BlockCyclicLayout):
 class BlockCyclicLu:
     """In-place distributed LU of the local column blocks (f64).  Returns (perm, info) device tensors."""
 
-    def __init__(self, layout: BlockCyclicLayout, group=None, lookahead: bool = True):
+    def __init__(self, layout: BlockCyclicLayout, group=None, lookahead: bool = True, p2p_first: bool = False):
         import torch
         from . import _lib
         self.layout = layout
@@ -108,7 +111,7 @@ class BlockCyclicLu:
         self.bufs = [torch.empty(HEADER_BYTES + n * layout.block * 8, dtype=torch.uint8, device=dev) for _ in range(nbuf)]
         # the next-next owner receives the panel twice (point-to-point first, then as a member of the broadcast): the second
         # copy lands in a scratch buffer so it never overwrites bytes its head update may be reading
-        self.p2p_first = self.lookahead and layout.world_size > 2
+        self.p2p_first = bool(p2p_first) and self.lookahead and layout.world_size > 2
         self.scratch = torch.empty_like(self.bufs[0]) if self.p2p_first else None
         self.comm2 = torch.cuda.Stream() if self.p2p_first else None     # carries the redundant broadcast copy only
         self.rowid = torch.empty(n, dtype=torch.int32, device=dev)

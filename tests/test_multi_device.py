@@ -116,6 +116,34 @@ def test_lu_sharded_bit_identical(rla, oracle):
     assert np.max(np.abs(r)) / (np.max(np.sum(np.abs(a), axis=1)) * np.max(np.abs(x)) * n * eps) <= 16
 
 
+def test_lu_sharded_pinned_streams_rows_back(rla, oracle):
+    """pinned host matrix + regular block-cyclic layout (n a multiple of 256 * N): finished block rows travel back during
+    the factorisation as strided 3-D copies.  Same bits as one GPU."""
+    if ngpu(rla) < 2:
+        pytest.skip("needs 2 GPUs in one process")
+    l = rla.lib()
+    n = 8192
+    a = oracle.fill_uniform((n, n), 12)
+    p = C.c_void_p()
+    assert l.rla_host_alloc_pinned(C.byref(p), a.nbytes) == 0
+    lu = np.frombuffer((C.c_char * a.nbytes).from_address(p.value), dtype=np.float64).reshape(n, n)
+    out = {}
+    for g in sorted({1, 2, ngpu(rla)}):
+        if n % (256 * g):
+            continue
+        assert l.rla_set_devices(g) == 0
+        lu[...] = a
+        perm = np.empty(n, dtype=np.uint64)
+        assert rla.check(l.rla_dgetrf(n, lu.ctypes.data, perm.ctypes.data)) == 0
+        out[g] = (lu.copy(), perm)
+    l.rla_set_devices(1)
+    for g in out:
+        assert np.array_equal(out[1][1], out[g][1]), f"perm differs at {g} GPUs"
+        assert np.array_equal(out[1][0], out[g][0]), f"factors differ at {g} GPUs"
+    del lu
+    l.rla_host_free_pinned(p)
+
+
 def test_lu_sharded_singular(rla, oracle):
     if ngpu(rla) < 2:
         pytest.skip("needs 2 GPUs in one process")

@@ -94,7 +94,7 @@ def test_block_cyclic_lu_world1_matches_getrf(oracle, n):
     assert int(info.item()) != 0
 
 
-def _nccl_worker(rank, world, port, n, lookahead, out_dir):
+def _nccl_worker(rank, world, port, n, lookahead, out_dir, p2p_first=False):
     import oracle
     import rulinalg_b200 as rla
     from rulinalg_b200.sharded_lu import BlockCyclicLu
@@ -106,7 +106,7 @@ def _nccl_worker(rank, world, port, n, lookahead, out_dir):
     lay = BlockCyclicLayout(n, world, rank)
     a = oracle.fill_uniform((n, n), 12)
     a_loc = torch.from_numpy(scatter_columns(a, lay)).cuda()
-    perm, info = BlockCyclicLu(lay, lookahead=lookahead).decompose(a_loc)
+    perm, info = BlockCyclicLu(lay, lookahead=lookahead, p2p_first=p2p_first).decompose(a_loc)
     torch.cuda.synchronize()
     np.save(os.path.join(out_dir, f"lu{rank}.npy"), a_loc.cpu().numpy())
     np.save(os.path.join(out_dir, f"perm{rank}.npy"), perm.cpu().numpy())
@@ -116,13 +116,14 @@ def _nccl_worker(rank, world, port, n, lookahead, out_dir):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("world,n,lookahead", [(2, 700, False), (2, 1280, True), (2, 2048, True),
-                                               (4, 2048, True), (4, 3000, True), (8, 4608, True)])
-def test_block_cyclic_lu_world2_nccl(tmp_path, oracle, world, n, lookahead):
-    """world > 2 also exercises the point-to-point-first path (the next-next owner gets the panel before the broadcast)"""
+@pytest.mark.parametrize("world,n,lookahead,p2p_first", [(2, 700, False, False), (2, 1280, True, False), (2, 2048, True, False),
+                                                         (4, 2048, True, False), (4, 3000, True, True), (8, 4608, True, False),
+                                                         (8, 4608, True, True)])
+def test_block_cyclic_lu_world2_nccl(tmp_path, oracle, world, n, lookahead, p2p_first):
+    """world > 2 with p2p_first also exercises the optional point-to-point-first path"""
     if torch.cuda.device_count() < world:
         pytest.skip(f"needs {world} GPUs")
-    mp.spawn(_nccl_worker, args=(world, _free_port(), n, lookahead, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_nccl_worker, args=(world, _free_port(), n, lookahead, str(tmp_path), p2p_first), nprocs=world, join=True)
     lay = BlockCyclicLayout(n, world, 0)
     got = gather_columns([np.load(tmp_path / f"lu{r}.npy") for r in range(world)], lay)
     perms = [np.load(tmp_path / f"perm{r}.npy") for r in range(world)]
