@@ -133,6 +133,11 @@ RLA_API void rla_lu_free(rla_lu_handle *h);
  * All pointers are device pointers on the current device; `stream` is a cudaStream_t passed
  * as void* (NULL = the CUDA legacy default stream, as in the runtime API).  Calls are asynchronous on that
  * stream unless stated.
+ * Workspaces: the LU / solve twins (rla_?getrf_dev, rla_?getrs_dev, rla_?getri_dev, rla_dlu_*_dev) use workspaces owned by
+ * the calling host thread's context on the current device (pivot packets and tags, row-origin vector, solve tickets).
+ * Keep at most ONE of them in flight per (host thread, device): enqueue the next one on the same stream, or synchronise
+ * in between.  The GEMM / GEMV / fill twins have no workspace and may overlap freely; rla_?potrf_dev takes its workspace
+ * from the caller.
  * ------------------------------------------------------------------------------------- */
 RLA_API int rla_init(int device);                 /* select device + create context; idempotent      */
 RLA_API int rla_device_count(void);
@@ -234,7 +239,7 @@ RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_
  * (see csrc/dgemm.cu).  "lu_gmax": cap on the panel kernel's row
  * CTAs.  "lu_cluster": 1 (default) = panels that fit one thread-block cluster use the DSMEM panel kernel, 0 = always
  * the grid-wide kernel.  "host_gemm_2d": 1 (default) = 2-D wavefront pipeline for large host-pointer products, 0 = row panels;
- * "host_gemm_s": strips per dimension of that pipeline, 0 (default) = auto.  "host_stage": 1 (default) = pageable host
+ * "host_gemm_s": strips per dimension of that pipeline, 0 (default) = auto.  "host_gemm_grade": 1 = graded (smaller) first and last strips in that pipeline (default 0: no measurable gain).  "host_stage": 1 (default) = pageable host
  * operands of large calls travel through the library's pinned staging ring (host.cu), 0 = plain cudaMemcpyAsync on them.
  * "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
 RLA_API int rla_set_tuning(const char *key, int value);
