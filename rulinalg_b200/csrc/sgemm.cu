@@ -92,6 +92,8 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
 
     const int tid = threadIdx.x;
     const int tx = tid & 15, ty = tid >> 4;      // ty < BM / 8: rows ty*4.. and BM/2 + ty*4..
+    // (measured and dropped: lanes as 4 ty x 8 tx -- a 32 x 64 warp tile, 4 instead of 6-8 shared-memory wavefronts per
+    // k-step -- 58.5 vs 59.5 TFLOP/s at 8192^3: shared-memory traffic is not what holds the FMA pipe at 80 %)
 
     // global->shared copy roles.  A: thread owns k-quad (tid&3) of rows (tid>>2) and (tid>>2)+BM/2.
     const int a_kq = (tid & 3) * 4, a_row = tid >> 2;
