@@ -128,6 +128,22 @@ RLA_API int rla_dgetrf_keep(size_t n, double *lu, size_t *perm, rla_lu_handle **
 RLA_API int rla_dlu_solve(const rla_lu_handle *h, double *b);
 RLA_API void rla_lu_free(rla_lu_handle *h);
 
+/* Held operands: device-resident GEMM operands across host-API calls (the reference multiplies by the
+ * same matrix repeatedly, e.g. lu.rs:789,907, eigen.rs:114-148).  matrixmultiply's signature cannot say "this operand has
+ * not changed since the last call", so the caller says it: between rla_operand_hold(host, bytes) and
+ * rla_operand_release(host) the byte range [host, host + bytes) is promised immutable (in Rust: a guard object that
+ * borrows `&Matrix<T>` for its lifetime -- the borrow checker enforces the promise; INTEGRATION.md shows it).  While a
+ * range is held, the first rla_dgemm / rla_sgemm that reads an A or B operand lying inside it (unit column stride, not
+ * the small-call or multi-GPU path) keeps that operand's device copy, and later calls with the same (pointer, rows,
+ * cols, row stride, element size) on the same device skip its host-to-device copy.  Results are bit-identical either
+ * way.  Holds nest (one release per hold of the same base; the byte count must match).  release frees the device
+ * copies; it must not run concurrently with a product that reads the range.  rla_shutdown drops all resident copies.
+ * If HBM has no room for a resident copy the call proceeds as if the range were not held.
+ * rla_operand_resident_bytes: device bytes currently kept for held operands (all devices). */
+RLA_API int rla_operand_hold(const void *host, size_t bytes);
+RLA_API int rla_operand_release(const void *host);
+RLA_API size_t rla_operand_resident_bytes(void);
+
 /* ---------------------------------------------------------------------------------------
  * Device-resident twins (kernel timing, multi-GPU sharding, LU -> solve reuse).
  * All pointers are device pointers on the current device; `stream` is a cudaStream_t passed

@@ -20,7 +20,7 @@ RLA_ERR_NO_DEVICE = -3
 SYMBOLS = [
     "rla_dgemm", "rla_sgemm", "rla_dgetrf", "rla_sgetrf", "rla_dgetrs", "rla_sgetrs",
     "rla_dgemv", "rla_sgemv", "rla_dgemv_dev", "rla_sgemv_dev", "rla_dtrsv", "rla_strsv", "rla_dgetri", "rla_sgetri", "rla_dgetri_dev", "rla_sgetri_dev",
-    "rla_dgetrf_keep", "rla_dlu_solve", "rla_lu_free",
+    "rla_dgetrf_keep", "rla_dlu_solve", "rla_lu_free", "rla_operand_hold", "rla_operand_release", "rla_operand_resident_bytes",
     "rla_dpotrf", "rla_spotrf", "rla_dpotrs", "rla_spotrs", "rla_dpotri", "rla_spotri",
     "rla_potrf_workspace_bytes", "rla_dpotrf_dev", "rla_spotrf_dev",
     "rla_init", "rla_device_count", "rla_set_devices", "rla_get_devices", "rla_shutdown", "rla_dev_alloc", "rla_dev_free", "rla_host_alloc_pinned",
@@ -80,6 +80,9 @@ def lib():
     l.rla_dlu_solve.argtypes = [P, P]
     l.rla_lu_free.argtypes = [P]
     l.rla_lu_free.restype = None
+    l.rla_operand_hold.argtypes = [P, sz]
+    l.rla_operand_release.argtypes = [P]
+    l.rla_operand_resident_bytes.restype = sz
     l.rla_init.argtypes = [i32]
     l.rla_set_devices.argtypes = [i32]
     l.rla_dev_alloc.argtypes = [C.POINTER(P), sz]

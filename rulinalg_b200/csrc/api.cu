@@ -180,6 +180,107 @@ int gemm_dev<float>(size_t m, size_t k, size_t n, float alpha, const float *a, s
     return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
 
+// ---- held operands (device-resident operands across host-API calls) --------------------------
+// An operand may stay resident in HBM across calls only if the library KNOWS it cannot have changed; behind
+// matrixmultiply's signature nothing says so, so the caller says it: rla_operand_hold(ptr, bytes) declares the host range
+// immutable until rla_operand_release(ptr) (in Rust: a guard that holds `&Matrix` -- the borrow checker then enforces the
+// promise).  While a range is held, the first product that reads an operand inside it keeps that operand's device copy, and
+// later calls with the same (pointer, shape, row stride) skip its H2D.
+namespace {
+struct HeldRegion { const unsigned char *base; size_t bytes; int refs; };
+struct HeldView { const void *p; size_t rows, cols, rs, elem; int device; void *dptr; };
+std::mutex g_held_mu;
+std::vector<HeldRegion> g_held_regions;
+std::vector<HeldView> g_held_views;
+
+bool held_covers(const void *p, size_t extent) {
+    std::lock_guard<std::mutex> lk(g_held_mu);
+    const unsigned char *q = static_cast<const unsigned char *>(p);
+    for (const HeldRegion &r : g_held_regions)
+        if (q >= r.base && q + extent <= r.base + r.bytes) return true;
+    return false;
+}
+void *held_lookup(const void *p, size_t rows, size_t cols, size_t rs, size_t elem, int device) {
+    std::lock_guard<std::mutex> lk(g_held_mu);
+    for (const HeldView &v : g_held_views)
+        if (v.p == p && v.rows == rows && v.cols == cols && v.rs == rs && v.elem == elem && v.device == device) return v.dptr;
+    return nullptr;
+}
+// registers a freshly filled device copy; returns false (caller frees its copy) when the range was released meanwhile or
+// another thread registered the same view first
+bool held_insert(const void *p, size_t extent, size_t rows, size_t cols, size_t rs, size_t elem, int device, void *dptr) {
+    std::lock_guard<std::mutex> lk(g_held_mu);
+    const unsigned char *q = static_cast<const unsigned char *>(p);
+    bool covered = false;
+    for (const HeldRegion &r : g_held_regions)
+        if (q >= r.base && q + extent <= r.base + r.bytes) covered = true;
+    if (!covered) return false;
+    for (const HeldView &v : g_held_views)
+        if (v.p == p && v.rows == rows && v.cols == cols && v.rs == rs && v.elem == elem && v.device == device) return false;
+    g_held_views.push_back(HeldView{p, rows, cols, rs, elem, device, dptr});
+    return true;
+}
+void held_free_views(const unsigned char *base, size_t bytes, bool all, const std::vector<HeldView> *keep = nullptr) {
+    std::vector<HeldView> drop;
+    {
+        std::lock_guard<std::mutex> lk(g_held_mu);
+        for (size_t i = 0; i < g_held_views.size();) {
+            const unsigned char *q = static_cast<const unsigned char *>(g_held_views[i].p);
+            bool kept = false;
+            if (keep)
+                for (const HeldView &kv : *keep) kept = kept || kv.dptr == g_held_views[i].dptr;
+            if (!kept && (all || (q >= base && q < base + bytes))) {
+                drop.push_back(g_held_views[i]);
+                g_held_views.erase(g_held_views.begin() + long(i));
+            } else ++i;
+        }
+    }
+    int cur = -1;
+    if (cudaGetDevice(&cur) != cudaSuccess) { (void)cudaGetLastError(); cur = -1; }
+    for (const HeldView &v : drop)
+        if (cudaSetDevice(v.device) == cudaSuccess) cudaFree(v.dptr);
+    (void)cudaGetLastError();
+    if (cur >= 0) cudaSetDevice(cur);
+}
+
+// One operand of a host-API call: resident (a held view exists), to be kept (held range, first use) or transient.
+template <typename T>
+struct Operand {
+    T *dev = nullptr;          // where the kernels read it
+    bool resident = false;     // device copy already valid: skip the H2D
+    bool fresh = false;        // allocated by this call for a held range: register on success, free otherwise
+    const void *host = nullptr;
+    size_t extent = 0, rows = 0, cols = 0, rs = 0;
+    int resolve(const T *h, bool packed, size_t rows_, size_t cols_, size_t rs_, size_t ld, Buffer &fallback, int device) {
+        host = h; rows = rows_; cols = cols_; rs = rs_;
+        extent = rows ? ((rows - 1) * rs + cols) * sizeof(T) : 0;
+        if (!packed && rows && cols && held_covers(h, extent)) {
+            if (void *v = held_lookup(h, rows, cols, rs, sizeof(T), device)) {
+                dev = static_cast<T *>(v);
+                resident = true;
+                return RLA_OK;
+            }
+            void *pnew = nullptr;
+            if (cudaMalloc(&pnew, rows * ld * sizeof(T)) == cudaSuccess) {
+                dev = static_cast<T *>(pnew);
+                fresh = true;
+                return RLA_OK;
+            }
+            (void)cudaGetLastError();          // no room for a resident copy: behave as if the range were not held
+        }
+        RLA_TRY(fallback.ensure((rows ? rows : 1) * ld * sizeof(T)));
+        dev = static_cast<T *>(fallback.p);
+        return RLA_OK;
+    }
+    void finish(bool ok, int device) {
+        if (!fresh) return;
+        if (!ok || !held_insert(host, extent, rows, cols, rs, sizeof(T), device, dev)) cudaFree(dev);
+        fresh = false;
+    }
+    bool owns(const T *dst, size_t ld) const { return dst >= dev && dst < dev + (rows ? rows : 1) * ld; }
+};
+}  // namespace
+
 namespace {
 
 cudaStream_t pick_stream(void *s) { return static_cast<cudaStream_t>(s); }   // NULL = CUDA legacy default stream
@@ -288,13 +389,16 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         RLA_TRY(gemm_host_multi<T>(m, k, n, alpha, ha, hrsa, hb, hrsb, hc, hrsc, stg));
     } else {
     const size_t lda = pad_ld(k ? k : 1, sizeof(T)), ldb = pad_ld(n, sizeof(T)), ldc = pad_ld(n, sizeof(T));
-    RLA_TRY(cx.dA.ensure(m * lda * sizeof(T)));
-    RLA_TRY(cx.dB.ensure((k ? k : 1) * ldb * sizeof(T)));
+    Operand<T> opA, opB;                       // held operands stay resident across calls (rla_operand_hold)
+    RLA_TRY(opA.resolve(ha, ha != a, k ? m : 0, k, hrsa, lda, cx.dA, cx.device));
+    RLA_TRY(opB.resolve(hb, hb != b, k, k ? n : 0, hrsb, ldb, cx.dB, cx.device));
     RLA_TRY(cx.dC.ensure(m * ldc * sizeof(T)));
-    T *dA = static_cast<T *>(cx.dA.p), *dB = static_cast<T *>(cx.dB.p), *dC = static_cast<T *>(cx.dC.p);
+    T *dA = opA.dev, *dB = opB.dev, *dC = static_cast<T *>(cx.dC.p);
     auto up = [&](T *dst, size_t ld, const T *src, size_t rs, size_t rows, size_t cols, bool pinned) -> int {
+        if ((opA.resident && opA.owns(dst, lda)) || (opB.resident && opB.owns(dst, ldb))) return RLA_OK;
         return stg.upload2d(dst, ld * sizeof(T), src, rs * sizeof(T), cols * sizeof(T), rows, pinned, cx.device, cx.copy_in);
     };
+    auto pipeline = [&]() -> int {
     auto down = [&](T *dst, size_t rs, const T *src, size_t ld, size_t rows, size_t cols) -> int {
         return stg.download2d(dst, rs * sizeof(T), src, ld * sizeof(T), cols * sizeof(T), rows, pin_c, cx.device, cx.copy_out);
     };
@@ -402,7 +506,18 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
     RLA_CUDA(cudaStreamSynchronize(cx.copy_out));
     RLA_CUDA(cudaStreamSynchronize(cx.stream));
     RLA_CUDA(cudaStreamSynchronize(cx.stream2));
-    RLA_TRY(stg.finish());           // pageable C: the last staged pieces are copied out by the drainer
+    return stg.finish();             // pageable C: the last staged pieces are copied out by the drainer
+    };
+    const int pst = pipeline();
+    if (pst != RLA_OK) {              // nothing may still be reading / writing the operand copies when they are freed
+        cudaStreamSynchronize(cx.copy_in);
+        cudaStreamSynchronize(cx.stream);
+        cudaStreamSynchronize(cx.stream2);
+        (void)cudaGetLastError();
+    }
+    opA.finish(pst == RLA_OK, cx.device);
+    opB.finish(pst == RLA_OK, cx.device);
+    RLA_TRY(pst);
     }
     if (!c_direct)
         for (size_t i = 0; i < m; ++i)
@@ -832,6 +947,53 @@ void rla_lu_free(rla_lu_handle *h) {
     delete h;
 }
 
+int rla_operand_hold(const void *host, size_t bytes) {
+    if (!host || bytes == 0) return RLA_ERR_INVALID;
+    std::lock_guard<std::mutex> lk(g_held_mu);
+    const unsigned char *q = static_cast<const unsigned char *>(host);
+    for (HeldRegion &r : g_held_regions)
+        if (r.base == q) {
+            if (r.bytes != bytes) return RLA_ERR_INVALID;    // the same base held twice must be the same range
+            ++r.refs;
+            return RLA_OK;
+        }
+    g_held_regions.push_back(HeldRegion{q, bytes, 1});
+    return RLA_OK;
+}
+int rla_operand_release(const void *host) {
+    const unsigned char *q = static_cast<const unsigned char *>(host);
+    size_t bytes = 0;
+    {
+        std::lock_guard<std::mutex> lk(g_held_mu);
+        size_t i = 0;
+        for (; i < g_held_regions.size(); ++i)
+            if (g_held_regions[i].base == q) break;
+        if (i == g_held_regions.size()) return RLA_ERR_INVALID;
+        if (--g_held_regions[i].refs > 0) return RLA_OK;
+        bytes = g_held_regions[i].bytes;
+        g_held_regions.erase(g_held_regions.begin() + long(i));
+    }
+    // device copies of views inside the range go, unless another held range still covers them
+    std::vector<HeldView> keep;
+    {
+        std::lock_guard<std::mutex> lk(g_held_mu);
+        for (const HeldView &v : g_held_views) {
+            const unsigned char *pv = static_cast<const unsigned char *>(v.p);
+            const size_t ext = ((v.rows - 1) * v.rs + v.cols) * v.elem;
+            for (const HeldRegion &r : g_held_regions)
+                if (pv >= r.base && pv + ext <= r.base + r.bytes) { keep.push_back(v); break; }
+        }
+    }
+    held_free_views(q, bytes, false, &keep);
+    return RLA_OK;
+}
+size_t rla_operand_resident_bytes(void) {
+    std::lock_guard<std::mutex> lk(g_held_mu);
+    size_t total = 0;
+    for (const HeldView &v : g_held_views) total += v.rows * pad_ld(v.cols, v.elem) * v.elem;
+    return total;
+}
+
 int rla_init(int device) { return ensure_ctx(device); }
 int rla_device_count(void) { return probe_device_count(); }
 int rla_set_devices(int n_gpus) { return multi_set_devices(n_gpus); }
@@ -841,6 +1003,7 @@ int rla_shutdown(void) {
     // multi-device contexts; everything is rebuilt lazily by the next call
     for (auto &c : tl_ctxs.per_dev) c.reset();
     multi_release();
+    held_free_views(nullptr, 0, true);               // resident operand copies (the held ranges themselves stay declared)
     return RLA_OK;
 }
 int rla_dev_alloc(void **p, size_t bytes) {

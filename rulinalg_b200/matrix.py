@@ -151,6 +151,38 @@ class _BaseMatrix:
     def sub_slice(self, start, rows, cols):
         return MatrixSlice.from_matrix(self, start, rows, cols)
 
+    def held(self):
+        """Guard (context manager) during which this matrix is promised immutable, so products that read it keep
+        its device copy and skip the upload on later calls (rla_operand_hold / rla_operand_release; SURVEY 8f rank 3,
+        the repeated products of lu.rs:789,907 and eigen.rs:114-148).  The Rust counterpart borrows `&Matrix<T>`."""
+        return _Held(self)
+
+
+class _Held:
+    def __init__(self, m: "_BaseMatrix"):
+        self._m = m
+        self._ptr = None
+
+    def __enter__(self):
+        a = self._m._arr
+        if a.size == 0:
+            return self._m
+        nbytes = ((a.shape[0] - 1) * (a.strides[0] // a.itemsize) + a.shape[1]) * a.itemsize
+        a.flags.writeable = False                      # numpy's stand-in for the shared borrow
+        self._ptr = a.ctypes.data
+        _lib.check(_lib.lib().rla_operand_hold(self._ptr, nbytes))
+        return self._m
+
+    def __exit__(self, *exc):
+        if self._ptr is not None:
+            _lib.check(_lib.lib().rla_operand_release(self._ptr))
+            try:
+                self._m._arr.flags.writeable = True
+            except ValueError:
+                pass
+            self._ptr = None
+        return False
+
 
 class Matrix(_BaseMatrix):
     """rulinalg::matrix::Matrix<T>: rows, cols, contiguous row-major data."""
@@ -174,10 +206,13 @@ class Matrix(_BaseMatrix):
         return m
 
     @staticmethod
-    def from_numpy(arr) -> "Matrix":
+    def from_numpy(arr, copy=True) -> "Matrix":
+        """copy=False adopts a C-contiguous f32/f64 array as the matrix's storage (Matrix::new takes the Vec by value)."""
         arr = np.asarray(arr)
         if arr.ndim != 2:
             raise Panic("expected a 2-D array")
+        if not copy and arr.flags.c_contiguous and arr.dtype in (np.float32, np.float64):
+            return Matrix._from_array(arr)
         return Matrix._from_array(np.array(arr, copy=True))
 
     @staticmethod

@@ -52,6 +52,31 @@ extern "C" {
     pub fn rla_device_count() -> i32;
     /// Returns the calling thread's streams / buffers / staging rings and the multi-GPU contexts (also runs at thread exit).
     pub fn rla_shutdown() -> i32;
+    /// Held operands: between hold and release the byte range is promised immutable, so products that
+    /// read an operand inside it keep the operand's device copy and skip its upload on later calls.
+    pub fn rla_operand_hold(host: *const ::std::os::raw::c_void, bytes: usize) -> i32;
+    pub fn rla_operand_release(host: *const ::std::os::raw::c_void) -> i32;
+    pub fn rla_operand_resident_bytes() -> usize;
+}
+
+/// `let _g = ffi::Held::new(&b);` -- while the guard lives, `b` is shared-borrowed (so nothing can mutate or drop it: the
+/// borrow checker enforces the promise the C ABI asks for) and every `&a * &b` re-uses b's copy in HBM instead of
+/// uploading it again (the repeated products of lu.rs:789,907, eigen.rs:114-148).  Dropping the guard frees the copy.
+pub struct Held<'a, T: 'a> {
+    data: &'a [T],
+}
+impl<'a, T> Held<'a, T> {
+    pub fn new(m: &'a ::matrix::Matrix<T>) -> Held<'a, T> {
+        let data = m.data().as_slice();
+        let st = unsafe { rla_operand_hold(data.as_ptr() as *const _, data.len() * ::std::mem::size_of::<T>()) };
+        assert!(st == RLA_OK, "librla_b200: rla_operand_hold -> {}", st);
+        Held { data: data }
+    }
+}
+impl<'a, T> Drop for Held<'a, T> {
+    fn drop(&mut self) {
+        unsafe { rla_operand_release(self.data.as_ptr() as *const _) };
+    }
 }
 
 /// Opt-in for multi-GPU boxes, e.g. from the embedding application's start-up:
