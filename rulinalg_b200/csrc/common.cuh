@@ -76,6 +76,8 @@ struct LuWorkspace {
     void *scratch = nullptr;      // panel scratch (candidates, barrier words, row buffers)
     size_t ipiv_cap = 0, scratch_cap = 0;
     unsigned tag = 0;             // next free packet tag (unique per panel column while scratch lives)
+    void *slab = nullptr;         // column-slab panel kernel: [64 headers | ticket | multiplier columns 64 x 4096 x 8 B]
+    unsigned slab_epoch = 0, slab_tickets = 0;   // launch counter (header validity) and CTAs launched so far (ticket base)
     cudaStream_t side = nullptr;  // high-priority stream for the look-ahead panel factorisation
     cudaEvent_t ev_head = nullptr, ev_fact = nullptr;
 };

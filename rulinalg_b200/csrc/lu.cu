@@ -1393,6 +1393,513 @@ lu_panel_cluster2_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int
 }
 
 // -------------------------------------------------------------------------------------------
+// Column-slab panel kernel (K3d): panels of <= 3840 rows, LEFT-looking across CTAs.
+//
+// The row-distributed kernels above pay one cross-CTA exchange per COLUMN (the pivot search needs every CTA's candidate):
+// ~2 us x 64 columns per panel whatever the panel height.  Here the 64 panel columns are dealt to the CTAs instead:
+// CTA k owns columns [k*NC, (k+1)*NC) of ALL rows (ROWS rows x NC columns per thread in registers, ROWS*NC = 32,
+// ROWS = 1/2/4/8 for panels of <= 480/960/1920/3840 rows => 2/4/8/16 CTAs), so the pivot search of a column is local to
+// one CTA (two warp reductions and ONE CTA barrier per column, the candidate rows staged speculatively per warp) and the
+// cross-CTA traffic is one-way: when a column is finished its owner publishes {pivot position, multiplier column}
+// through L2 (multipliers: plain stores; then a release store of a 64-bit header epoch << 32 | position), and every CTA
+// that owns later columns applies it (a[r][j] -= m[r] * u[j], u = its own columns' values in the pivot row, broadcast
+// through shared memory with one barrier) at its own pace -- nobody ever answers.  The dependency chain of a panel is
+// 64 local column steps + (number of CTAs) hand-overs instead of 64 exchanges.
+//   * arithmetic and pivot rule are those of K3 / K3b (unfused multiply and subtract, updates of an element in
+//     ascending column order, first maximum in the swapped ordering wins, NaN never wins unless it is the diagonal,
+//     |pivot| < eps -> info): factors, permutation and status are bit-identical (asserted in tests);
+//   * implicit pivoting as in K3b: rows never move, every CTA tracks each row's position in the reference's
+//     swapped ordering; the panel is written back permuted at the end;
+//   * a 16th warp per CTA keeps the books so the 15 worker warps never wait for anything but data: it polls the
+//     headers of foreign columns (ld.acquire.gpu) and hands them to the workers through shared memory, publishes the
+//     CTA's own columns (the workers count themselves done in shared memory; st.release.gpu by this warp is the only
+//     gpu-scope fence in the kernel), and folds every pivot into the panel's net permutation (and, in CTA 0, into the
+//     outer block's plan) as it goes;
+//   * no cluster, no cooperative launch: CTAs take a ticket on entry and logical CTA k only ever waits for logical
+//     CTAs < k, all of which are running by then.
+// -------------------------------------------------------------------------------------------
+constexpr int SL_WORKERS = 480;                  // 15 worker warps + the bookkeeping warp = 512 threads => 128 registers each
+constexpr int SL_WARPS = SL_WORKERS / 32;        // (a 17-warp CTA is capped at 96: one scheduler would hold five warps)
+constexpr int SL_THREADS = SL_WORKERS + 32;
+constexpr int SL_MAXROWS = 8 * SL_WORKERS;       // 3840
+constexpr int SL_GPASS = (2 * PW * CL_GC + SL_WORKERS - 1) / SL_WORKERS;   // closing gather: entries per thread and pass
+struct SlabScratch {
+    unsigned long long *hdr;     // [PW]  epoch << 32 | pivot position (0xffffffff: |pivot| < eps)
+    unsigned *ticket;            // monotonic CTA counter (never reset; the host passes this launch's base)
+    void *mbuf;                  // [PW][rstride] multiplier columns, indexed by row slot
+    unsigned epoch, ticket_base;
+    int rstride;
+};
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned ld_acquire_cta_s(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_cta_s(unsigned *p, unsigned v) {
+    asm volatile("st.release.cta.shared.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void red_release_cta_s(unsigned *p, unsigned v) {
+    asm volatile("red.release.cta.shared.add.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ void slab_worker_sync() { asm volatile("bar.sync 1, %0;" ::"n"(SL_WORKERS) : "memory"); }
+
+template <typename T, int ROWS>
+__global__ void __launch_bounds__(SL_THREADS, 1)
+lu_panel_slab_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int32_t *__restrict__ ipiv,
+                     int32_t *__restrict__ info, PanelScratch sc, SlabScratch ss, int J0, int w, int dbg) {
+    constexpr int NC = 32 / ROWS;
+    constexpr int VN = 16 / int(sizeof(T));                 // elements per 16-byte shared-memory access
+    struct alignas(16) Vec { T v[VN]; };
+    __shared__ __align__(16) T ubuf[2][NC];                 // pivot row of a foreign column, my NC columns
+    __shared__ __align__(16) T wrow[2][SL_WARPS][NC];       // own columns: every warp's candidate row (speculative)
+    __shared__ unsigned long long wkey[2][SL_WARPS];
+    __shared__ int widx[2][SL_WARPS];
+    __shared__ int piv_sm[PW];                              // pivot position per column (-1: singular)
+    __shared__ int own_piv[NC];
+    __shared__ unsigned ready, done_cnt;                    // columns known (bookkeeper -> workers); worker warps done (-> bookkeeper)
+    __shared__ int sh_k, sh_skip, sh_nt;
+    __shared__ PlanState st;                                // hub CTA: the outer block's plan state
+    __shared__ int dst_l[2 * PW], src_l[2 * PW];            // the panel's net permutation: row dst_l[e] <- old row src_l[e]
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        sh_k = int(atomicAdd(ss.ticket, 1u) - ss.ticket_base);
+        sh_skip = (*info != 0);
+        ready = 0u;
+        done_cnt = 0u;
+        sh_nt = 0;
+    }
+    __syncthreads();
+    if (sh_skip) return;
+    const int k = sh_k;
+    unsigned long long *const tr = (w == PW) ? sc.trace : nullptr;   // optional %globaltimer stamps (lu_dbg bit 3)
+    if (tr && tid == 0) tr[1536 + 8 * k + 0] = gtime();
+    const int ncta = (jb + NC - 1) / NC;                    // column CTAs; logical CTA ncta is the hub
+    if (k >= ncta) {
+        // ---------------- the hub CTA: one warp follows the headers and folds every pivot into the outer block's
+        // net-permutation plan (consumed by rowid_apply_kernel / laswp_apply_kernel); nobody waits for it ----------------
+        if (warp != 0) return;
+        int nf_g = 0;
+        if (J == J0) {
+            for (int i = lane; i < w; i += 32) st.od[i] = i;
+        } else {
+            for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                st.od[i] = sc.state->od[i];
+                st.fr[i] = sc.state->fr[i];
+                st.of[i] = sc.state->of[i];
+            }
+            nf_g = sc.state->nf;
+        }
+        __syncwarp();
+        for (int c = 0; c < jb; ++c) {
+            unsigned long long h;
+            do {
+                h = ld_relaxed_gpu(&ss.hdr[c]);
+                h = __shfl_sync(0xffffffffu, h, 0);
+            } while (unsigned(h >> 32) != ss.epoch);
+            const int p = int(unsigned(h));
+            if (p < 0) return;                               // singular: the owner has set *info, the plan is not needed
+            fold_pivot(st.od, st.fr, st.of, nf_g, J0, w, J + c, p, lane);
+        }
+        if (J + jb != J0 + w) {
+            for (int i = lane; i < LASWP_MAXJB; i += 32) {
+                sc.state->od[i] = st.od[i];
+                sc.state->fr[i] = st.fr[i];
+                sc.state->of[i] = st.of[i];
+            }
+            if (lane == 0) sc.state->nf = nf_g;
+        } else {
+            const int nt = w + nf_g;
+            if (lane == 0) sc.plan->nt = nt;
+            for (int i = lane; i < nt; i += 32) {
+                sc.plan->rows[i] = (i < w) ? J0 + i : st.fr[i - w];
+                sc.plan->origin[i] = (i < w) ? st.od[i] : st.of[i - w];
+            }
+        }
+        return;
+    }
+    const int c0 = k * NC;                                  // my first column (panel-relative)
+    const int nown = min(NC, jb - c0);
+    const int nrows = n - J;
+    const size_t RS = size_t(ss.rstride);
+    T *const mbuf = static_cast<T *>(ss.mbuf);
+
+    if (tid >= SL_WORKERS) {
+        // ---------------- the bookkeeping warp ----------------
+        // Columns become KNOWN in order: own columns when all worker warps have counted themselves done (every column
+        // finished by then is published behind ONE gpu-scope fence), foreign columns when their header shows this
+        // launch's epoch; known columns are handed to the workers at once.
+        int nknown = 0;
+        while (nknown < jb) {
+            const int c = nknown;
+            if (c >= c0 && c < c0 + nown) {
+                const int ndone = int(ld_acquire_cta_s(&done_cnt)) / SL_WARPS;           // own columns complete
+                const int nnew = c0 + ndone - c;
+                if (nnew <= 0) continue;
+                if (lane == 0 && tr) for (int q = 0; q < nnew; ++q) tr[(c + q) * 8 + 2] = gtime();
+                if (lane < nnew) {
+                    const int p = own_piv[c - c0 + lane];
+                    if (p < 0) *info = J + c + lane + 1; else ipiv[J + c + lane] = p;       // lu.rs:179-183
+                    piv_sm[c + lane] = p;
+                }
+                __syncwarp();
+                __threadfence();                             // the workers' multiplier columns (cumulativity) before the headers
+                int stop = nnew;
+                bool sing = false;
+                for (int q = 0; q < nnew; ++q) {
+                    const int p = piv_sm[c + q];
+                    if (lane == 0) st_relaxed_gpu(&ss.hdr[c + q], ((unsigned long long)ss.epoch << 32) | (unsigned long long)(unsigned)p);
+                    if (p < 0) { sing = true; stop = q + 1; break; }
+                }
+                if (lane == 0 && tr) for (int q = 0; q < stop; ++q) { tr[(c + q) * 8 + 3] = gtime(); tr[(c + q) * 8 + 7] = (unsigned long long)(unsigned)piv_sm[c + q]; }
+                nknown = c + stop;
+                __syncwarp();
+                if (lane == 0) st_release_cta_s(&ready, unsigned(nknown));
+                if (sing) break;
+            } else {
+                unsigned long long h = ld_relaxed_gpu(&ss.hdr[c]);
+                h = __shfl_sync(0xffffffffu, h, 0);
+                if (unsigned(h >> 32) != ss.epoch) continue;
+                __threadfence();                             // acquire: the multiplier column behind the header
+                const int p = int(unsigned(h));
+                if (tr && lane == 0 && c0 == (c / NC + 1) * NC) tr[c * 8 + 4] = gtime();   // the next owner saw it
+                if (lane == 0) piv_sm[c] = p;
+                __syncwarp();
+                nknown = c + 1;
+                if (lane == 0) st_release_cta_s(&ready, unsigned(nknown));
+                if (p < 0) break;
+            }
+        }
+        return;
+    }
+
+    // ---------------- workers: thread tid keeps row slots tid, tid + 480, ... of my NC columns ----------------
+    // The column steps are ISSUE-bound (15 warps x a few hundred instructions per column on 4 schedulers), so the row
+    // loops are written branch-free: predicated selects instead of per-row branches, floating-point comparisons for the
+    // candidate search, one reciprocal per column + five FMAs per row (div_via_rcp: bit-identical to the IEEE division)
+    // instead of a division per row when a thread holds four or more rows.
+    int pos[ROWS];
+    unsigned act = 0u;                                       // bit r: row r not picked yet
+    T a[ROWS][NC];
+    // My slab of the panel is nrows segments of NC*sizeof(T) bytes: moved between global memory and registers through
+    // shared memory in 16-byte chunks so that every 32-byte sector is requested exactly once (a thread reading its own
+    // row with scalar loads requests each sector four times: ~8 us per CTA instead of ~2).
+    extern __shared__ __align__(16) unsigned char slab_smem[];
+    T *const stg = reinterpret_cast<T *>(slab_smem);         // [row slot][NC + VN]
+    constexpr int SLD = NC + VN, LPR = NC / VN;
+    const bool vec_io = nown == NC && ((size_t(ld) * sizeof(T)) & 15) == 0 &&
+                        (reinterpret_cast<size_t>(A + size_t(J) * ld + J + c0) & 15) == 0;
+    if (vec_io) {
+        for (int q = tid; q < nrows * LPR; q += SL_WORKERS) {
+            const int row = q / LPR, part = q % LPR;
+            *reinterpret_cast<Vec *>(stg + size_t(row) * SLD + part * VN) =
+                *reinterpret_cast<const Vec *>(A + size_t(J + row) * ld + J + c0 + part * VN);
+        }
+        slab_worker_sync();
+    }
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int s = tid + SL_WORKERS * r;
+        const bool has = s < nrows;
+        pos[r] = J + s;
+        if (has) act |= 1u << r;
+        if (vec_io) {
+#pragma unroll
+            for (int jv = 0; jv < NC; jv += VN) {
+                Vec t;
+#pragma unroll
+                for (int e = 0; e < VN; ++e) t.v[e] = T(0);
+                if (has) t = *reinterpret_cast<const Vec *>(stg + size_t(s) * SLD + jv);
+#pragma unroll
+                for (int e = 0; e < VN; ++e) a[r][jv + e] = t.v[e];
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < NC; ++j) a[r][j] = (has && j < nown) ? A[size_t(J + s) * ld + J + c0 + j] : T(0);
+        }
+    }
+    T m[ROWS];
+    bool sing = false;
+    unsigned known = 0u;
+
+    // ---- columns of the CTAs before me, one at a time, as they are published ----
+    {
+        bool have = false;                                   // m[] already holds column c (requested during column c - 1)
+        for (int c = 0; c < c0; ++c) {
+            if (unsigned(c) + 1u >= known) {
+                known = ld_acquire_cta_s(&ready);
+                while (known <= unsigned(c)) known = ld_acquire_cta_s(&ready);
+            }
+            const int p = piv_sm[c];
+            if (p < 0) { sing = true; break; }
+            if (!have) {
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) m[r] = __ldcg(mbuf + size_t(c) * RS + tid + SL_WORKERS * r);
+            }
+            const int d = J + c, par = c & 1;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const bool on = (act >> r) & 1u;
+                const bool isp = on && pos[r] == p;          // I hold the pivot row: it retires to position d
+                const bool isd = pos[r] == d;                // (only a live row can sit at d)
+                if (isp) {
+#pragma unroll
+                    for (int jv = 0; jv < NC; jv += VN) {
+                        Vec t;
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) t.v[e] = a[r][jv + e];
+                        *reinterpret_cast<Vec *>(&ubuf[par][jv]) = t;
+                    }
+                }
+                pos[r] = isp ? d : (isd ? p : pos[r]);
+                act &= ~(unsigned(isp) << r);
+            }
+            slab_worker_sync();
+            if (tr && tid == 0 && c0 == (c / NC + 1) * NC) tr[c * 8 + 5] = gtime();        // the next owner's workers start applying it
+            have = (c + 1 < c0) && (unsigned(c) + 1u < known);          // uniform per warp
+            constexpr int UCH = NC < 8 ? NC : 8;
+#pragma unroll
+            for (int j0 = 0; j0 < NC; j0 += UCH) {
+                T u[UCH];
+#pragma unroll
+                for (int jv = 0; jv < UCH; jv += VN) {
+                    const Vec t = *reinterpret_cast<const Vec *>(&ubuf[par][j0 + jv]);
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) u[jv + e] = t.v[e];
+                }
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    if ((act >> r) & 1u) {
+#pragma unroll
+                        for (int jj = 0; jj < UCH; ++jj) a[r][j0 + jj] = sub_rn(a[r][j0 + jj], mul_rn(m[r], u[jj]));
+                    }
+                    // the multiplier of this row in the next column: requested now, consumed one column later
+                    if (j0 + UCH == NC && have) m[r] = __ldcg(mbuf + size_t(c + 1) * RS + tid + SL_WORKERS * r);
+                }
+            }
+        }
+    }
+
+    // ---- my own columns: pivot search local to this CTA ----
+#pragma unroll
+    for (int i = 0; i < NC; ++i) {
+        if (i < nown && !sing) {
+            const int c = c0 + i, d = J + c, par = i & 1;
+            if (tr && tid == 0) tr[c * 8 + 0] = gtime();
+            // my best row: first maximum of |a| in the swapped ordering; a NaN never wins unless it is the diagonal
+            // (lu.rs:170-178); "no candidate" = (-1, INT_MAX)
+            T bav = T(-1);
+            int bidx = INT_MAX, br = 0;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                T av = fabs(a[r][i]);
+                if (!(av == av) && pos[r] == d) av = T(CUDART_INF);
+                const bool gt = ((act >> r) & 1u) && (av > bav || (av == bav && pos[r] < bidx));
+                bav = gt ? av : bav;
+                bidx = gt ? pos[r] : bidx;
+                br = gt ? r : br;
+            }
+            unsigned long long wk = key_of(double(bav));
+            int wi = bidx;
+            unsigned wm;
+            warp_argmax(wk, wi, wm);
+            if (lane == 0) { wkey[par][warp] = wk; widx[par][warp] = wi; }
+            if (bidx == wi && wi != INT_MAX) {                           // the one lane that holds the warp's candidate row
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    if (r == br) {
+#pragma unroll
+                        for (int jv = (i / VN) * VN; jv < NC; jv += VN) {
+                            Vec t;
+#pragma unroll
+                            for (int e = 0; e < VN; ++e) t.v[e] = a[r][jv + e];
+                            *reinterpret_cast<Vec *>(&wrow[par][warp][jv]) = t;
+                        }
+                    }
+                }
+            }
+            slab_worker_sync();
+            unsigned long long gk = (lane < SL_WARPS) ? wkey[par][lane] : 0ull;
+            int gi = (lane < SL_WARPS) ? widx[par][lane] : INT_MAX;
+            unsigned gm;
+            warp_argmax(gk, gi, gm);
+            const int ww = gm ? __ffs(gm) - 1 : 0;
+            const bool sing_now = T(__longlong_as_double((long long)gk)) < Eps<T>::v();      // lu.rs:179-183
+            if (tr && tid == 0) tr[c * 8 + 1] = gtime();
+            if (tid == 0) own_piv[i] = sing_now ? -1 : gi;
+            if (sing_now) {
+                sing = true;
+            } else {
+                const int p = gi;
+                const T *u = &wrow[par][ww][0];
+                const T piv = u[i];
+                T y = T(0);
+                if (ROWS >= 4) y = rcp_rn(piv);
+#pragma unroll
+                for (int r = 0; r < ROWS; ++r) {
+                    const bool on = (act >> r) & 1u;
+                    const bool isp = on && pos[r] == p;
+                    const bool isd = pos[r] == d;
+                    pos[r] = isp ? d : (isd ? p : pos[r]);
+                    act &= ~(unsigned(isp) << r);
+                    const T mm = (ROWS >= 4) ? div_via_rcp(a[r][i], piv, y) : div_rn(a[r][i], piv);
+                    if (on && !isp) {
+                        a[r][i] = mm;
+                        m[r] = mm;
+                        __stcg(mbuf + size_t(c) * RS + tid + SL_WORKERS * r, mm);
+                    }
+                }
+                if (NC <= 8) {
+                    T ur[NC];
+#pragma unroll
+                    for (int jv = ((i + 1) / VN) * VN; jv < NC; jv += VN) {
+                        const Vec t = *reinterpret_cast<const Vec *>(u + jv);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) ur[jv + e] = t.v[e];
+                    }
+#pragma unroll
+                    for (int r = 0; r < ROWS; ++r) {
+                        if ((act >> r) & 1u) {
+#pragma unroll
+                            for (int j = i + 1; j < NC; ++j) a[r][j] = sub_rn(a[r][j], mul_rn(m[r], ur[j]));
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int jv = ((i + 1) / VN) * VN; jv < NC; jv += VN) {
+                        const Vec t = *reinterpret_cast<const Vec *>(u + jv);
+#pragma unroll
+                        for (int e = 0; e < VN; ++e) {
+                            if (jv + e > i) {
+#pragma unroll
+                                for (int r = 0; r < ROWS; ++r)
+                                    if ((act >> r) & 1u) a[r][jv + e] = sub_rn(a[r][jv + e], mul_rn(m[r], t.v[e]));
+                            }
+                        }
+                    }
+                }
+            }
+            if (tr && tid == 0) tr[c * 8 + 6] = gtime();
+            __syncwarp();
+            if (lane == 0) red_release_cta_s(&done_cnt, 1u);
+        }
+    }
+
+    // ---- the pivots of the columns after mine only move my rows' positions ----
+    if (!sing) {
+        for (int c = c0 + nown; c < jb; ++c) {
+            if (unsigned(c) >= known) {
+                known = ld_acquire_cta_s(&ready);
+                while (known <= unsigned(c)) known = ld_acquire_cta_s(&ready);
+            }
+            const int p = piv_sm[c];
+            if (p < 0) { sing = true; break; }
+            const int d = J + c;
+#pragma unroll
+            for (int r = 0; r < ROWS; ++r) {
+                const bool isp = ((act >> r) & 1u) && pos[r] == p;
+                const bool isd = pos[r] == d;
+                pos[r] = isp ? d : (isd ? p : pos[r]);
+                act &= ~(unsigned(isp) << r);
+            }
+        }
+    }
+    if (tr && tid == 0) tr[1536 + 8 * k + 1] = gtime();
+    if (sing) return;                                        // uniform over the workers (and over the CTAs)
+    // the panel's net permutation, straight from the rows' positions: row pos[r] <- old row J + s wherever they differ
+#pragma unroll
+    for (int r = 0; r < ROWS; ++r) {
+        const int s = tid + SL_WORKERS * r;
+        if (s < nrows && pos[r] != J + s) {
+            const int e = atomicAdd(&sh_nt, 1);
+            dst_l[e] = pos[r];
+            src_l[e] = J + s;
+        }
+    }
+    if (tr && tid == 0) tr[1536 + 8 * k + 2] = gtime();
+    // write my columns back, every row at its final position
+    if (vec_io) {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int s = tid + SL_WORKERS * r;
+            if (s < nrows) {
+#pragma unroll
+                for (int jv = 0; jv < NC; jv += VN) {
+                    Vec t;
+#pragma unroll
+                    for (int e = 0; e < VN; ++e) t.v[e] = a[r][jv + e];
+                    *reinterpret_cast<Vec *>(stg + size_t(pos[r] - J) * SLD + jv) = t;
+                }
+            }
+        }
+        slab_worker_sync();
+        for (int q = tid; q < nrows * LPR; q += SL_WORKERS) {
+            const int row = q / LPR, part = q % LPR;
+            *reinterpret_cast<Vec *>(A + size_t(J + row) * ld + J + c0 + part * VN) =
+                *reinterpret_cast<const Vec *>(stg + size_t(row) * SLD + part * VN);
+        }
+    } else {
+#pragma unroll
+        for (int r = 0; r < ROWS; ++r) {
+            const int s = tid + SL_WORKERS * r;
+            if (s < nrows) {
+#pragma unroll
+                for (int j = 0; j < NC; ++j)
+                    if (j < nown) A[size_t(pos[r]) * ld + J + c0 + j] = a[r][j];
+            }
+        }
+    }
+    if (tr && tid == 0) tr[1536 + 8 * k + 3] = gtime();
+    slab_worker_sync();                                      // the list of moved rows is complete
+    // the panel's interchanges on the outer block's columns outside the panel: one gather, split over the CTAs
+    if (!(dbg & 1)) {
+        const int na = J - J0, ncols = na + (J0 + w - J - jb);     // columns [J0, J) and [J + jb, J0 + w)
+        const int cpc = (ncols + ncta - 1) / ncta;
+        const int c_lo = k * cpc, c_hi = min(ncols, c_lo + cpc);
+        const int nt = sh_nt;
+        for (int g0 = c_lo; g0 < c_hi; g0 += CL_GC) {             // uniform per CTA
+            T v[SL_GPASS];
+            bool mv[SL_GPASS];
+#pragma unroll
+            for (int uu = 0; uu < SL_GPASS; ++uu) {
+                const int e = tid + SL_WORKERS * uu, i = e / CL_GC, t2 = g0 + (e % CL_GC);
+                mv[uu] = i < nt && t2 < c_hi;
+                if (mv[uu]) {
+                    const int col = (t2 < na) ? J0 + t2 : J + jb + (t2 - na);
+                    v[uu] = A[size_t(src_l[i]) * ld + col];
+                }
+            }
+            slab_worker_sync();                                     // every source is read before any destination is written
+#pragma unroll
+            for (int uu = 0; uu < SL_GPASS; ++uu) {
+                const int e = tid + SL_WORKERS * uu, i = e / CL_GC, t2 = g0 + (e % CL_GC);
+                if (mv[uu]) {
+                    const int col = (t2 < na) ? J0 + t2 : J + jb + (t2 - na);
+                    A[size_t(dst_l[i]) * ld + col] = v[uu];
+                }
+            }
+        }
+    }
+    if (tr && tid == 0) tr[1536 + 8 * k + 4] = gtime();
+}
+
+// -------------------------------------------------------------------------------------------
 // laswp for a whole outer block: interchanges (J+k <-> ipiv[J+k]), k = 0..jb-1 (jb <= 256), applied
 // to the columns left and right of the block as ONE gather instead of jb dependent swaps.
 //   plan kernel (one warp): simulate the interchanges on indices.  "Touched" rows: index i < jb ->
@@ -1599,6 +2106,7 @@ unsigned long long *g_lu_trace = nullptr;
 int g_lu_gmax_ref();
 int g_lu_dbg_ref();
 int g_lu_cluster_ref();
+int g_lu_slab_rows_ref();
 
 // scratch layout (bytes): packets | rowbuf | diagbuf | result | laswp plan | plan state
 constexpr size_t SC_PACKETS = 0;
@@ -1647,6 +2155,60 @@ PanelScratch scratch_view(LuWorkspace &ws) {
     sc.rowid = nullptr;
     sc.trace = nullptr;
     return sc;
+}
+
+constexpr size_t SLAB_HDR_BYTES = PW * sizeof(unsigned long long);
+constexpr size_t SLAB_MBUF_OFF = 1024;
+constexpr size_t SLAB_BYTES = SLAB_MBUF_OFF + size_t(PW) * SL_MAXROWS * sizeof(double);
+
+template <typename T, int ROWS>
+int launch_slab_rows(const SlabScratch &ss, T *a, size_t ld, int n, int j, int jb, int32_t *ipiv, int32_t *d_info,
+                     const PanelScratch &sc, int J0, int w, int ncta, cudaStream_t s) {
+    constexpr int NC = 32 / ROWS, VN = 16 / int(sizeof(T));
+    constexpr size_t smem = size_t(ROWS) * SL_WORKERS * (NC + VN) * sizeof(T);       // staging for the slab's load / write-back
+    static DeviceOnce attr_once;
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_slab_kernel<T, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+        attr_once.done(od_);
+    }
+    lu_panel_slab_kernel<T, ROWS><<<ncta + 1, SL_THREADS, smem, s>>>(a, ld, n, j, jb, ipiv, d_info, sc, ss, J0, w, g_lu_dbg_ref());
+    RLA_LAUNCHED();
+    return RLA_OK;
+}
+
+template <typename T>
+int launch_slab_panel(LuWorkspace &ws, T *a, size_t ld, int n, int j, int jb, int32_t *ipiv, int32_t *d_info,
+                      const PanelScratch &sc, int J0, int w, cudaStream_t s) {
+    if (!ws.slab) {
+        RLA_CUDA(cudaMalloc(&ws.slab, SLAB_BYTES));
+        RLA_CUDA(cudaMemsetAsync(ws.slab, 0, SLAB_MBUF_OFF, s));
+        ws.slab_epoch = 0;
+        ws.slab_tickets = 0;
+    }
+    const int nrem = n - j;
+    int rows = 1;
+    while (rows * SL_WORKERS < nrem) rows *= 2;
+    const int nc = 32 / rows, ncta = (jb + nc - 1) / nc;
+    unsigned char *base = static_cast<unsigned char *>(ws.slab);
+    SlabScratch ss;
+    ss.hdr = reinterpret_cast<unsigned long long *>(base);
+    ss.ticket = reinterpret_cast<unsigned *>(base + SLAB_HDR_BYTES);
+    ss.mbuf = base + SLAB_MBUF_OFF;
+    ss.epoch = ++ws.slab_epoch;                 // never 0: a zeroed header is never valid
+    if (ws.slab_epoch == 0xffffffffu) {         // wrap: start over with clean headers
+        RLA_CUDA(cudaMemsetAsync(ws.slab, 0, SLAB_HDR_BYTES, s));
+        ws.slab_epoch = 0;
+        ss.epoch = ++ws.slab_epoch;
+    }
+    ss.ticket_base = ws.slab_tickets;
+    ws.slab_tickets += unsigned(ncta + 1);      // + the hub CTA; wraps together with the device counter (unsigned arithmetic)
+    ss.rstride = rows * SL_WORKERS;
+    switch (rows) {
+    case 1: return launch_slab_rows<T, 1>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
+    case 2: return launch_slab_rows<T, 2>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
+    case 4: return launch_slab_rows<T, 4>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
+    default: return launch_slab_rows<T, 8>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
+    }
 }
 
 // Factor the outer block whose diagonal starts at (J0, J0) of `a` (w <= 256 columns, rows J0..n-1).
@@ -1704,6 +2266,11 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
         const int jb = min(PW, J0 + w - j);
         const int nrem = n - j;
         if (trace_base) sc.trace = trace_base + size_t((j - J0) / PW) * 64 * 8;   // one page per inner panel
+        // panels of <= 4096 rows, column-slab kernel: columns dealt to the CTAs, pivot search local to one CTA
+        const int slab_rows = g_lu_cluster_ref() == 3 ? SL_MAXROWS : (g_lu_cluster_ref() == 1 ? min(g_lu_slab_rows_ref(), SL_MAXROWS) : 0);
+        if (nrem <= slab_rows) {
+            RLA_TRY(launch_slab_panel<T>(ws, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, s));
+        } else
         // panels of <= 16 x 256 rows: one thread-block cluster, panel in registers, exchange over DSMEM
         if (g_lu_cluster_ref() && nrem <= cluster_max * CL_ROWS) {
             int CS = 1;
@@ -1807,8 +2374,13 @@ int g_lu_gmax = 32;           // rla_set_tuning("lu_gmax", v): cap on the grid p
                               // rows fit in shared memory).  The panel is latency-bound, its CTAs only take SMs from the overlapped
                               // Schur update: tools/lu_gmax_sweep.py, n = 16384: 120.9 / 128.0 / 133.1 ms at 32 / 112 / 147
 int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bit0: hub skips row swaps, bit2: no look-ahead)
-int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", v): 0 = always the grid-wide panel kernel; 1 (default) = panels that fit one thread-block cluster use the DSMEM pull kernel; 2 = the pushed-row cluster kernel (experimental: bit-identical, measured slower)
-namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } }
+int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", v): panel kernel selection.  0 = always the grid-wide kernel (K3);
+                               // 1 (default) = automatic: column-slab kernel (K3d) for panels of <= lu_slab_rows rows, cluster pull
+                               // kernel (K3b) up to 4096 rows, K3 above; 2 = pushed-row cluster kernel (K3c, experimental: bit-identical,
+                               // measured slower); 3 = K3d wherever it fits (<= 3840 rows), K3b / K3 above; 4 = K3b / K3 only
+int g_lu_slab_rows = 960;      // rla_set_tuning("lu_slab_rows", v): tallest panel the automatic rule gives to K3d (measured crossover
+                               // against K3b: profiles/r02_lu_slab_sweep.jsonl)
+namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } int g_lu_slab_rows_ref() { return g_lu_slab_rows; } }
 
 int device_num_sms() {
     static std::atomic<int> sms[RLA_MAX_DEVICES];
@@ -1824,6 +2396,7 @@ int device_num_sms() {
 void lu_workspace_release(LuWorkspace &ws) {
     if (ws.ipiv) cudaFree(ws.ipiv);
     if (ws.scratch) cudaFree(ws.scratch);
+    if (ws.slab) cudaFree(ws.slab);
     if (ws.side) cudaStreamDestroy(ws.side);
     if (ws.ev_head) cudaEventDestroy(ws.ev_head);
     if (ws.ev_fact) cudaEventDestroy(ws.ev_fact);

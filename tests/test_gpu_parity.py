@@ -350,8 +350,9 @@ def test_lu_pivot_rule_ties_and_nan(rla, oracle):
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_lu_cluster_panel_identical_to_grid_panel(rla, oracle, dtype):
-    """The two panel kernels (grid-wide exchange through L2; one thread-block cluster with the panel in registers and
-    the exchange over DSMEM) must produce bit-identical factors, permutations and status: same pivot rule
+    """The panel kernels (grid-wide exchange through L2; one thread-block cluster with the panel in registers and
+    the exchange over DSMEM, pull and push variants; column slabs with a CTA-local pivot search and one-way hand-overs
+    through L2) must produce bit-identical factors, permutations and status: same pivot rule
     (lu.rs:170-178), same unfused arithmetic.  Sizes cover 1/2/4/8/16-CTA clusters, ragged last panels, the hand-over
     from the grid kernel (n > 4096), ties, a NaN diagonal and a singular matrix."""
     import torch
@@ -386,7 +387,7 @@ def test_lu_cluster_panel_identical_to_grid_panel(rla, oracle, dtype):
         cases.append(sing)
         for a in cases:
             g = factor(a, 0)
-            for mode in (1, 2):                 # DSMEM pull kernel; pushed-row kernel
+            for mode in (1, 2, 3, 4):           # automatic (slab + pull); pushed-row; column-slab wherever it fits; pull only
                 c = factor(a, mode)
                 assert g[2] == c[2], (a.shape, mode)
                 if g[2] == 0:
@@ -411,9 +412,10 @@ def test_multiplier_division_is_ieee(rla, f32, mode):
 
 
 def test_lu_panel_kernels_randomized_stress(rla, oracle):
-    """a long randomized A/B run of the three panel kernels (grid exchange through L2 with hashed
-    self-validating messages; cluster pull; cluster push).  60 seeded matrices with sizes that hit every cluster
-    size and ragged panels, each factored by all three: bit-identical factors, permutations, status."""
+    """a long randomized A/B run of the panel kernels (grid exchange through L2 with hashed
+    self-validating messages; cluster pull; cluster push; column slabs).  60 seeded matrices with sizes that hit every
+    cluster size, every slab shape and ragged panels, each factored by all of them: bit-identical factors, permutations,
+    status."""
     import torch
     l = rla.lib()
     s = torch.cuda.current_stream().cuda_stream
@@ -433,7 +435,7 @@ def test_lu_panel_kernels_randomized_stress(rla, oracle):
             n = int(rng.choice([130, 256, 300, 511, 640, 1000, 1500, 2048, 2500, 3333, 4096]))
             a0 = torch.from_numpy(oracle.fill_uniform((n, n), 9000 + trial, np.float64, lo=-0.5, scale=1.0)).cuda()
             g = factor(a0, 0)
-            for mode in (1, 2):
+            for mode in (1, 2, 3, 4):
                 c = factor(a0, mode)
                 torch.cuda.synchronize()
                 assert int(g[2].item()) == int(c[2].item()) == 0
