@@ -570,7 +570,7 @@ def extras(rla, l, torch, np, dev, sptr, peak64, peak32):
             tf = 2.0 * m * k * n / ms * 1e-9
             out[f"{name}_{m}x{k}x{n}"] = {"ms": ms, "tflops": tf, "frac_of_peak": tf / peak}
             del a, b, c
-    for n in (4096, 8192, 32768):
+    for n in (1024, 2048, 4096, 8192, 32768):
         a0 = torch.empty(n, n, dtype=torch.float64, device=dev)
         rla.check(l.rla_fill_uniform_f64_dev(a0.data_ptr(), n, n, n, 12, 0, 0.0, 1.0, sptr))
         a = torch.empty_like(a0)

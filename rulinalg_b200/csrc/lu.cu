@@ -1758,8 +1758,8 @@ lu_panel_slab_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int32_t
                     const bool isd = pos[r] == d;
                     pos[r] = isp ? d : (isd ? p : pos[r]);
                     act &= ~(unsigned(isp) << r);
-                    const T mm = (ROWS >= 4) ? div_via_rcp(a[r][i], piv, y) : div_rn(a[r][i], piv);
-                    if (on && !isp) {
+                    if (on && !isp) {                        // (rows past the panel's end hold zeros: they would take div_via_rcp's slow path)
+                        const T mm = (ROWS >= 4) ? div_via_rcp(a[r][i], piv, y) : div_rn(a[r][i], piv);
                         a[r][i] = mm;
                         m[r] = mm;
                         __stcg(mbuf + size_t(c) * RS + tid + SL_WORKERS * r, mm);
@@ -2378,7 +2378,7 @@ int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", v): panel kernel 
                                // 1 (default) = automatic: column-slab kernel (K3d) for panels of <= lu_slab_rows rows, cluster pull
                                // kernel (K3b) up to 4096 rows, K3 above; 2 = pushed-row cluster kernel (K3c, experimental: bit-identical,
                                // measured slower); 3 = K3d wherever it fits (<= 3840 rows), K3b / K3 above; 4 = K3b / K3 only
-int g_lu_slab_rows = 960;      // rla_set_tuning("lu_slab_rows", v): tallest panel the automatic rule gives to K3d (measured crossover
+int g_lu_slab_rows = 1920;     // rla_set_tuning("lu_slab_rows", v): tallest panel the automatic rule gives to K3d (measured crossover
                                // against K3b: profiles/r02_lu_slab_sweep.jsonl)
 namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } int g_lu_slab_rows_ref() { return g_lu_slab_rows; } }
 

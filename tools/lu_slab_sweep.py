@@ -14,7 +14,7 @@ for dt, fn, fill in ((torch.float64, l.rla_dgetrf_dev, l.rla_fill_uniform_f64_de
         perm = torch.empty(n, dtype=torch.int64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
         out = dict(dtype=str(dt)[6:], n=n)
         rla.check(l.rla_set_tuning(b"lu_cluster", 1))
-        for thr in (0, 480, 960, 1920, 3840):
+        for thr in (0, 960, 1440, 1920):
             rla.check(l.rla_set_tuning(b"lu_slab_rows", thr))
             best = 1e30
             for _ in range(5):
@@ -25,4 +25,4 @@ for dt, fn, fill in ((torch.float64, l.rla_dgetrf_dev, l.rla_fill_uniform_f64_de
             out[f"ms_slab_rows_{thr}"] = round(best, 4)
         out["info"] = int(info.item())
         print(json.dumps(out), flush=True)
-rla.check(l.rla_set_tuning(b"lu_slab_rows", 960))
+rla.check(l.rla_set_tuning(b"lu_slab_rows", 1920))
