@@ -1430,11 +1430,6 @@ struct SlabScratch {
     unsigned epoch, ticket_base;
     int rstride;
 };
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -1442,9 +1437,6 @@ __device__ __forceinline__ unsigned long long ld_relaxed_gpu(const unsigned long
 }
 __device__ __forceinline__ void st_relaxed_gpu(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ void st_release_gpu(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ unsigned ld_acquire_cta_s(const unsigned *p) {
     unsigned v;
@@ -2201,14 +2193,18 @@ int launch_slab_panel(LuWorkspace &ws, T *a, size_t ld, int n, int j, int jb, in
         ss.epoch = ++ws.slab_epoch;
     }
     ss.ticket_base = ws.slab_tickets;
-    ws.slab_tickets += unsigned(ncta + 1);      // + the hub CTA; wraps together with the device counter (unsigned arithmetic)
     ss.rstride = rows * SL_WORKERS;
+    int st = RLA_OK;
     switch (rows) {
-    case 1: return launch_slab_rows<T, 1>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
-    case 2: return launch_slab_rows<T, 2>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
-    case 4: return launch_slab_rows<T, 4>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
-    default: return launch_slab_rows<T, 8>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s);
+    case 1: st = launch_slab_rows<T, 1>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s); break;
+    case 2: st = launch_slab_rows<T, 2>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s); break;
+    case 4: st = launch_slab_rows<T, 4>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s); break;
+    default: st = launch_slab_rows<T, 8>(ss, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, ncta, s); break;
     }
+    // every CTA of a launch that went out takes exactly one ticket (the hub CTA included); a refused launch takes none.
+    // The host count wraps together with the device counter (unsigned arithmetic).
+    if (st == RLA_OK) ws.slab_tickets += unsigned(ncta + 1);
+    return st;
 }
 
 // Factor the outer block whose diagonal starts at (J0, J0) of `a` (w <= 256 columns, rows J0..n-1).
