@@ -15,7 +15,7 @@
 
 namespace rla {
 
-extern int g_dgemm_cfg;   // dgemm.cu
+extern int g_dgemm_cfg, g_dgemm_streamk;   // dgemm.cu
 extern int g_sgemm_cfg;   // sgemm.cu
 extern int g_lu_gmax, g_lu_dbg, g_lu_cluster, g_lu_slab_rows;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
@@ -1136,6 +1136,11 @@ int rla_measure_peak(int kind, double *tflops) {
 
 int rla_set_tuning(const char *key, int value) {
     if (!key) return RLA_ERR_INVALID;
+    if (strcmp(key, "dgemm_streamk") == 0) {
+        if (value < 0 || value > 3) return RLA_ERR_INVALID;
+        g_dgemm_streamk = value;
+        return RLA_OK;
+    }
     if (strcmp(key, "dgemm_cfg") == 0) {
         if (value < -1 || value > 7) return RLA_ERR_INVALID;
         g_dgemm_cfg = value;

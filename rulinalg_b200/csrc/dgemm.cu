@@ -26,6 +26,8 @@
 //   Tiles are rasterised in bands of 16 tile-rows so co-resident CTAs share A and B slabs in L2.
 //   beta == 0 never reads C (mat_mul.rs:52-55 hands over uninitialised memory); beta != 0 loads C in
 //   batches of 8 independent 16-byte loads before the FMAs (rank-k updates are epilogue-heavy).
+#include <mutex>
+
 #include "common.cuh"
 
 namespace rla {
@@ -280,6 +282,205 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
     }
 }
 
+// -------------------------------------------------------------------------------------------
+// Stream-K variant for products whose tile count does not fill the machine evenly (BASELINE config C1, 1024^3: 256 tiles
+// of 64x64 put two tiles on 108 SMs and one on 40 -- 86.5 % at best, 65 % measured).  Work unit = (tile, k-slab); CTA b of g
+// takes the contiguous units [b*U/g, (b+1)*U/g), i.e. every SM gets the same number of k-slabs whatever the tile count.
+// A segment that covers a whole tile is written straight to C; a partial segment stores its accumulators to a workspace
+// slot (a CTA has at most two: slot 2b = its first segment, 2b+1 = its last), and a fix-up kernel (one CTA per split tile)
+// adds the slots of the tile in ascending CTA = ascending k order and applies alpha / beta.  The summation order is
+// fixed by (shape, grid), so results are deterministic; they differ from the one-tile-one-CTA kernel in the last bits
+// (partial sums over k ranges), inside the same error bound.
+// -------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ long long sk_u0(long long b, long long U, long long g) { return b * U / g; }
+
+template <class C>
+__device__ __forceinline__ void tile_coords(int tile, int tiles_m, int tiles_n, int &m0, int &n0) {
+    const int per_band = BAND * tiles_n;
+    const int band = tile / per_band;
+    const int rem = tile - band * per_band;
+    const int band_rows = min(BAND, tiles_m - band * BAND);
+    m0 = (band * BAND + rem % band_rows) * C::BM;
+    n0 = (rem / band_rows) * C::BN;
+}
+
+// C tile <- alpha*acc + beta*C (the epilogue of dgemm_dmma_kernel as a function; beta == 0 never reads C)
+template <class C>
+__device__ __forceinline__ void write_tile(const double (&acc)[C::MT][C::NT][2], double alpha, double beta, double *Cmat,
+                                           size_t ldc, int M, int N, int m0, int n0, int wm, int wn, int g, int t) {
+    const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cmat) & 15) == 0);
+#pragma unroll
+    for (int i = 0; i < C::MT; ++i) {
+        const int row = m0 + wm * C::MT * 8 + i * 8 + g;
+        if (row >= M) continue;
+        double *crow = Cmat + size_t(row) * ldc;
+#pragma unroll
+        for (int j = 0; j < C::NT; ++j) {
+            const int col = n0 + wn * C::NT * 8 + j * 8 + 2 * t;
+            if (col >= N) continue;
+            double v0 = alpha * acc[i][j][0];
+            double v1 = alpha * acc[i][j][1];
+            if (col + 1 < N && vec_ok) {
+                if (beta != 0.0) {
+                    const double2 old = *reinterpret_cast<const double2 *>(crow + col);
+                    v0 += beta * old.x;
+                    v1 += beta * old.y;
+                }
+                *reinterpret_cast<double2 *>(crow + col) = make_double2(v0, v1);
+            } else {
+                if (beta != 0.0) v0 += beta * crow[col];
+                crow[col] = v0;
+                if (col + 1 < N) {
+                    if (beta != 0.0) v1 += beta * crow[col + 1];
+                    crow[col + 1] = v1;
+                }
+            }
+        }
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS, C::MINB)
+dgemm_streamk_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, size_t lda,
+                     const double *__restrict__ B, size_t ldb, double beta, double *__restrict__ Cmat, size_t ldc,
+                     int tiles_m, int tiles_n, double *__restrict__ ws) {
+    extern __shared__ __align__(16) double smem[];
+    double *As = smem;
+    double *Bs = smem + C::STAGES * C::A_STAGE;
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % C::WM, wn = warp / C::WM;
+    const int KT = (K + C::BK - 1) / C::BK;
+    const int KT_FULL = K / C::BK;
+    const uint32_t as_u32 = smem_u32(As), bs_u32 = smem_u32(Bs);
+    const double *a_frag_base = As + (wm * C::MT * 8 + g) * C::LDAS + t;
+    const double *b_frag_base = Bs + t * C::LDBS + wn * C::NT * 8 + g;
+
+    const long long U = (long long)tiles_m * tiles_n * KT, G = gridDim.x, b = blockIdx.x;
+    long long u = sk_u0(b, U, G);
+    const long long uend = sk_u0(b + 1, U, G);
+    bool first = true;
+    while (u < uend) {
+        const int tile = int(u / KT);
+        const int kt0 = int(u - (long long)tile * KT);
+        const int kt1 = int(min((long long)KT, kt0 + (uend - u)));
+        int m0, n0;
+        tile_coords<C>(tile, tiles_m, tiles_n, m0, n0);
+
+        CopyPlan<C> plan;
+        {
+            using P = CopyPlan<C>;
+            const int arow = tid / P::ACH, ach = tid % P::ACH;
+            plan.a_k = 2 * ach;
+            plan.a_dst = (arow * C::LDAS + 2 * ach) * 8;
+            plan.a_step = size_t(P::A_ROWS) * lda;
+            plan.a_valid = 0;
+#pragma unroll
+            for (int i = 0; i < C::A_CHUNKS; ++i)
+                if (m0 + arow + i * P::A_ROWS < M) plan.a_valid |= 1u << i;
+            plan.a_src = A + size_t(m0 + arow) * lda + 2 * ach;
+            const int brow = tid / P::BCH, bch = tid % P::BCH;
+            plan.b_k = brow;
+            plan.b_dst = (brow * C::LDBS + 2 * bch) * 8;
+            plan.b_step = size_t(P::B_ROWS) * ldb;
+            const int gn = n0 + 2 * bch;
+            plan.b_bytes = gn + 1 < N ? 16 : (gn < N ? 8 : 0);
+            plan.b_src = B + size_t(brow) * ldb + (gn < N ? gn : 0);
+        }
+        double acc[C::MT][C::NT][2];
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        const int nseg = kt1 - kt0;
+#pragma unroll
+        for (int s = 0; s < C::STAGES - 1; ++s) {
+            if (s < nseg)
+                issue_slab<C, true>(plan, as_u32 + s * C::A_STAGE * 8, bs_u32 + s * C::B_STAGE * 8, (kt0 + s) * C::BK, K, ldb,
+                                    kt0 + s < KT_FULL, A, B, lda, M, N, m0, n0, tid);
+            cp_async_commit();
+        }
+        int stage = 0;
+        for (int i = 0; i < nseg; ++i) {
+            cp_async_wait<C::STAGES - 2>();
+            __syncthreads();
+            const double *ap = a_frag_base + stage * C::A_STAGE;
+            const double *bp = b_frag_base + stage * C::B_STAGE;
+            mma_k4<C>(acc, ap, bp, 0);
+            {
+                const int ni = i + C::STAGES - 1;
+                if (ni < nseg) {
+                    int ns = stage + C::STAGES - 1;
+                    if (ns >= C::STAGES) ns -= C::STAGES;
+                    issue_slab<C, true>(plan, as_u32 + ns * C::A_STAGE * 8, bs_u32 + ns * C::B_STAGE * 8, (kt0 + ni) * C::BK, K,
+                                        ldb, kt0 + ni < KT_FULL, A, B, lda, M, N, m0, n0, tid);
+                }
+                cp_async_commit();
+            }
+#pragma unroll
+            for (int kk = 4; kk < C::BK; kk += 4) mma_k4<C>(acc, ap, bp, kk);
+            if (++stage == C::STAGES) stage = 0;
+        }
+        cp_async_wait<0>();
+        __syncthreads();                          // the next segment's prologue overwrites the stages
+
+        if (kt0 == 0 && kt1 == KT) {
+            write_tile<C>(acc, alpha, beta, Cmat, ldc, M, N, m0, n0, wm, wn, g, t);
+        } else {
+            double *slot = ws + size_t(2 * b + (first ? 0 : 1)) * (C::BM * C::BN);
+#pragma unroll
+            for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+                for (int j = 0; j < C::NT; ++j)
+                    *reinterpret_cast<double2 *>(slot + (size_t(i * C::NT + j) * C::THREADS + tid) * 2) =
+                        make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+        first = false;
+        u += nseg;
+    }
+}
+
+template <class C>
+__global__ void __launch_bounds__(C::THREADS)
+dgemm_streamk_fixup_kernel(int M, int N, int K, double alpha, double beta, double *__restrict__ Cmat, size_t ldc, int tiles_m,
+                           int tiles_n, const double *__restrict__ ws, int G) {
+    const int tile = blockIdx.x;
+    const int KT = (K + C::BK - 1) / C::BK;
+    const long long U = (long long)tiles_m * tiles_n * KT;
+    const long long ua = (long long)tile * KT, ub = ua + KT;
+    long long bf = ua * G / U, bl = (ub - 1) * G / U;             // CTAs that hold the tile's first and last unit
+    while (sk_u0(bf + 1, U, G) <= ua) ++bf;
+    while (sk_u0(bf, U, G) > ua) --bf;
+    while (sk_u0(bl + 1, U, G) <= ub - 1) ++bl;
+    while (sk_u0(bl, U, G) > ub - 1) --bl;
+    if (bf == bl) return;                                          // one CTA had the whole tile and wrote it itself
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int wm = warp % C::WM, wn = warp / C::WM;
+    double acc[C::MT][C::NT][2];
+#pragma unroll
+    for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+        for (int j = 0; j < C::NT; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (long long b = bf; b <= bl; ++b) {                         // ascending CTA = ascending k: a fixed summation order
+        const double *slot = ws + size_t(2 * b + (sk_u0(b, U, G) >= ua ? 0 : 1)) * (C::BM * C::BN);
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i)
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) {
+                const double2 p = *reinterpret_cast<const double2 *>(slot + (size_t(i * C::NT + j) * C::THREADS + tid) * 2);
+                acc[i][j][0] += p.x;
+                acc[i][j][1] += p.y;
+            }
+    }
+    int m0, n0;
+    tile_coords<C>(tile, tiles_m, tiles_n, m0, n0);
+    write_tile<C>(acc, alpha, beta, Cmat, ldc, M, N, m0, n0, wm, wn, g, t);
+}
+
 // k == 0: C <- beta*C, zero-fill when beta == 0 without reading C.
 template <typename T>
 __global__ void scale_c_kernel(size_t M, size_t N, T beta, T *C, size_t ldc) {
@@ -308,9 +509,73 @@ int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size
     return RLA_OK;
 }
 
+// The library's own stream-ordered memory pool, one per device, never trimmed: a freed workspace is handed to the next
+// product without a trip to the driver (the device's default pool releases at every synchronisation: ~400 us per call).
+int streamk_pool(cudaMemPool_t *out) {
+    static std::mutex mu;
+    static cudaMemPool_t pools[RLA_MAX_DEVICES] = {};
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lk(mu);
+    if (!pools[dev]) {
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        RLA_CUDA(cudaMemPoolCreate(&pools[dev], &props));
+        unsigned long long keep = ~0ull;
+        RLA_CUDA(cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &keep));
+    }
+    *out = pools[dev];
+    return RLA_OK;
+}
+
+template <class C>
+int launch_streamk(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
+                   double beta, double *c, size_t ldc, cudaStream_t st) {
+    static DeviceOnce attr_once;
+    const int tiles_m = int((m + C::BM - 1) / C::BM), tiles_n = int((n + C::BN - 1) / C::BN);
+    if (const int od_ = attr_once.pending(); od_ >= 0) {
+        RLA_CUDA(cudaFuncSetAttribute(dgemm_streamk_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+        RLA_CUDA(cudaFuncSetAttribute(dgemm_streamk_kernel<C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        attr_once.done(od_);
+    }
+    const long long KT = (long long)((k + C::BK - 1) / C::BK), U = (long long)tiles_m * tiles_n * KT;
+    long long grid = (long long)device_num_sms() * C::MINB;
+    if (grid > U) grid = U;
+    // stream-ordered workspace: two accumulator slots per CTA; safe for concurrent products on different streams
+    cudaMemPool_t pool = nullptr;
+    RLA_TRY(streamk_pool(&pool));
+    double *ws = nullptr;
+    RLA_CUDA(cudaMallocFromPoolAsync(reinterpret_cast<void **>(&ws), size_t(2) * size_t(grid) * C::BM * C::BN * sizeof(double), pool, st));
+    dgemm_streamk_kernel<C><<<unsigned(grid), C::THREADS, C::SMEM, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb, beta, c,
+                                                                         ldc, tiles_m, tiles_n, ws);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) {
+        note_launch();
+        dgemm_streamk_fixup_kernel<C><<<unsigned(tiles_m * tiles_n), C::THREADS, 0, st>>>(int(m), int(n), int(k), alpha, beta, c,
+                                                                                          ldc, tiles_m, tiles_n, ws, int(grid));
+        e = cudaGetLastError();
+        if (e == cudaSuccess) note_launch();
+    }
+    cudaFreeAsync(ws, st);                      // stream-ordered: released after the fix-up kernel
+    if (e != cudaSuccess) {
+        note_cuda_error(e);
+        return RLA_ERR_CUDA;
+    }
+    return RLA_OK;
+}
+
 }  // namespace
 
 int g_dgemm_cfg = -1;  // -1 = auto (cost model below); rla_set_tuning("dgemm_cfg", 0..7) forces one
+int g_dgemm_streamk = 0;   // rla_set_tuning("dgemm_streamk", v): 0 (default) = tiled kernels only; 2 = 128x128 stream-K whenever the
+                           // operands are aligned, 3 = 64x64 stream-K.  Off by default on the evidence of
+                           // profiles/r02_dgemm_streamk_sweep.jsonl: it wins 5-10 % where the tile count quantises badly AND k is long
+                           // (1280^3, 1792^3, 1024x4096x1024), ties from 2048^3 up and LOSES at 512^3-1024^3 (1024^3: main kernel 77 us
+                           // + fix-up 17 us against 85 us tiled under ncu) -- short k ranges per CTA refill the cp.async ring per segment
+                           // and the 27 MB of partial tiles are reduced by only 64 CTAs.  It would also end the shape-independence of
+                           // every C element's rounding that the pipelines and the multi-GPU paths rely on for bit-identity.
 
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st) {
@@ -337,6 +602,10 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
     // four CTAs per SM: 4x finer tail, shorter pipeline fill) from a two-term cost model fitted to the
     // measured table in profiles/r01_dgemm_cfg_table.md:  cost = waves * tile_work / (e_inf * k / (k + k0)).
     int cfg = g_dgemm_cfg;
+    if (aligned && cfg < 0 && g_dgemm_streamk >= 2) {
+        return g_dgemm_streamk == 2 ? launch_streamk<CfgW16K32>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st)
+                                    : launch_streamk<CfgTiny>(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+    }
     if (cfg < 0) {
         if (aligned) {
             const double t128 = double((m + 127) / 128) * double((n + 127) / 128);

@@ -208,6 +208,32 @@ def test_gemm_host_2d_wavefront_pipeline(rla, oracle, dtype):
     check_gemm(oracle, a, b, got2d, positive=True)
 
 
+@pytest.mark.parametrize("mode", [2, 3])
+def test_gemm_streamk_variant_vs_oracle(rla, oracle, mode):
+    # the opt-in stream-K DGEMM (rla_set_tuning("dgemm_streamk", 2 | 3); off by default): uneven k ranges per CTA,
+    # partial tiles reduced in ascending k order by a fix-up kernel.  Same error bound as the tiled kernels (ragged shapes,
+    # alpha / beta, one-CTA-per-tile and many-CTAs-per-tile cases), and run-to-run deterministic.
+    l = rla.lib()
+    try:
+        for (m, k, n), alpha, beta in (((300, 1000, 200), 1.0, 0.0), ((129, 77, 513), -1.5, 0.75), ((1024, 1024, 1024), 1.0, 0.0),
+                                       ((64, 4096, 64), 1.0, 1.0), ((2048, 96, 2048), 1.0, 0.0)):
+            a = oracle.fill_uniform((m, k), 31, np.float64)
+            b = oracle.fill_uniform((k, n), 32, np.float64)
+            c0 = oracle.fill_uniform((m, n), 33, np.float64)
+            assert l.rla_set_tuning(b"dgemm_streamk", mode) == 0
+            got = gpu_gemm_dev(rla, a, b, alpha=alpha, beta=beta, c=c0.copy())
+            again = gpu_gemm_dev(rla, a, b, alpha=alpha, beta=beta, c=c0.copy())
+            assert l.rla_set_tuning(b"dgemm_streamk", 0) == 0
+            tiled = gpu_gemm_dev(rla, a, b, alpha=alpha, beta=beta, c=c0.copy())
+            assert np.array_equal(got, again)
+            bound = 2 * gamma(k + 2, np.float64) * (abs(alpha) * (np.abs(a) @ np.abs(b)) + abs(beta) * np.abs(c0))
+            assert np.all(np.abs(got - tiled) <= 2 * bound)
+            ref = alpha * oracle.gemm(a, b) + beta * c0
+            assert np.all(np.abs(got - ref) <= 2 * bound)
+    finally:
+        l.rla_set_tuning(b"dgemm_streamk", 0)
+
+
 def test_gemm_degenerate(rla):
     # m*n == 0 -> no-op; k == 0 with beta == 0 -> zero fill
     assert (rla.Matrix.zeros(0, 3) * rla.Matrix.zeros(3, 4)).rows() == 0
