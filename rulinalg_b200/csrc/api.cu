@@ -20,6 +20,9 @@ extern int g_sgemm_cfg;   // sgemm.cu
 extern int g_lu_gmax, g_lu_dbg, g_lu_cluster, g_lu_slab_rows;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 int g_host_gemm_s = 0;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline; 0 = auto (~512-row strips)
+int g_host_gemm_kprefix = -1;     // rla_set_tuning("host_gemm_kprefix", v): f64 2-D pipeline, fraction of k (in 1/16) uploaded and multiplied as
+                                  // rank-kc updates of ALL of C before the wavefront starts; -1 = auto (k/4 when k >= 4096), 0 = off
+int g_host_gemm_kchunk = 256;     // rla_set_tuning("host_gemm_kchunk", kc): depth of those rank-kc updates (measured 256 / 512 / 1024: 35.7 / 36.1 / 37.2 ms)
 int g_host_gemm_grade = 0;        // rla_set_tuning("host_gemm_grade", 0/1): graded first / last strips of that pipeline (off: measured 37.9 vs 38.2 ms at 8192^3 pinned -- the start-up loss is the quadratic growth of computable work, not the strip size)
 int g_host_stage = 1;             // rla_set_tuning("host_stage", 0/1): pageable operands through the pinned staging ring (host.cu)
 
@@ -178,6 +181,16 @@ template <>
 int gemm_dev<float>(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b,
                     size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
     return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
+}
+// C <- alpha * (C + A*B), bit-identical continuation of a k-split product (f64 only: dgemm.cu ACC_C)
+template <typename T> constexpr bool gemm_has_acc() { return false; }
+template <> constexpr bool gemm_has_acc<double>() { return true; }
+template <typename T>
+int gemm_dev_acc(size_t, size_t, size_t, T, const T *, size_t, const T *, size_t, T *, size_t, cudaStream_t) { return RLA_ERR_INVALID; }
+template <>
+int gemm_dev_acc<double>(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
+                         double *c, size_t ldc, cudaStream_t st) {
+    return dgemm_launch(m, k, n, alpha, a, lda, b, ldb, 0.0, c, ldc, st, true);
 }
 
 // ---- held operands (device-resident operands across host-API calls) --------------------------
@@ -439,17 +452,50 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         boundaries(n, pn, cb);
         const size_t sm = rb.size() - 1, sn = cb.size() - 1;
         const size_t steps = sm > sn ? sm : sn;
-        while (cx.events.size() < 3 * steps + 1) {
+        // k-prefix (f64): the wavefront makes work available QUADRATICALLY in the uploaded bytes (a C tile needs a whole row
+        // panel and a whole column chunk), which starves the GPU for the first ~6 ms at 8192^3.  Rank-kc updates of ALL of C
+        // need only kc columns of A and kc rows of B each -- work LINEAR in the bytes -- so the first k1 = k/4 of the k
+        // range is uploaded and multiplied that way (chunk 0 plain, later chunks continuing the accumulators: ACC_C), and the
+        // wavefront then runs on the remaining k range while the GPU still has the prefix to chew on.  Every C element is
+        // still ONE accumulation chain in k order => bit-identical to the plain pipelines (asserted in tests).
+        // Measured at 8192^3: 38.3 -> 35.7 ms pinned, 44.1 -> 41.6 ms pageable (profiles/r02_e2e_kprefix_probe.jsonl).
+        size_t k1 = 0, kc = size_t(g_host_gemm_kchunk > 0 ? g_host_gemm_kchunk : 256) / 32 * 32;
+        if (kc == 0) kc = 32;
+        if (gemm_has_acc<T>() && g_host_gemm_kprefix != 0) {
+            const size_t sixteenths = g_host_gemm_kprefix < 0 ? 4 : size_t(g_host_gemm_kprefix > 15 ? 15 : g_host_gemm_kprefix);
+            if (g_host_gemm_kprefix > 0 || k >= 4096) k1 = (k * sixteenths / 16) / kc * kc;
+            if (k1 + 1024 > k) k1 = 0;
+        }
+        const size_t nchunk = k1 / kc;
+        while (cx.events.size() < 3 * steps + nchunk + 2) {
             cudaEvent_t e;
             RLA_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
             cx.events.push_back(e);
         }
+        for (size_t ch = 0; ch < nchunk; ++ch) {
+            const size_t kk = ch * kc;
+            RLA_TRY(up(dA + kk, lda, ha + kk, hrsa, m, kc, pin_a));
+            RLA_TRY(up(dB + kk * ldb, ldb, hb + kk * hrsb, hrsb, kc, n, pin_b));
+            cudaEvent_t ev = cx.events[3 * steps + 1 + ch];
+            RLA_CUDA(cudaEventRecord(ev, cx.copy_in));
+            RLA_CUDA(cudaStreamWaitEvent(cx.stream, ev, 0));
+            if (ch == 0) RLA_TRY(gemm_dev<T>(m, kc, n, T(1), dA, lda, dB, ldb, T(0), dC, ldc, cx.stream));
+            else RLA_TRY(gemm_dev_acc<T>(m, kc, n, T(1), dA + kk, lda, dB + kk * ldb, ldb, dC, ldc, cx.stream));
+        }
+        cudaEvent_t ev_prefix = cx.events[3 * steps + 1 + nchunk];
+        if (k1) RLA_CUDA(cudaEventRecord(ev_prefix, cx.stream));
+        const size_t kr = k - k1;                       // k range of the wavefront
+        auto tile_gemm = [&](size_t mm, size_t nn, const T *pa, const T *pb, T *pc, cudaStream_t strm) -> int {
+            if (k1 == 0) return gemm_dev<T>(mm, k, nn, alpha, pa, lda, pb, ldb, beta, pc, ldc, strm);
+            return gemm_dev_acc<T>(mm, kr, nn, alpha, pa + k1, lda, pb + k1 * ldb, ldb, pc, ldc, strm);
+        };
+        if (k1) RLA_CUDA(cudaStreamWaitEvent(cx.stream2, ev_prefix, 0));
         for (size_t st = 0; st < steps; ++st) {
             const size_t r0 = st < sm ? rb[st] : m, c0 = st < sn ? cb[st] : n;
             const size_t rows = st < sm ? rb[st + 1] - r0 : 0;
             const size_t cols = st < sn ? cb[st + 1] - c0 : 0;
-            if (rows) RLA_TRY(up(dA + r0 * lda, lda, ha + r0 * hrsa, hrsa, rows, k, pin_a));
-            if (cols) RLA_TRY(up(dB + c0, ldb, hb + c0, hrsb, k, cols, pin_b));
+            if (rows) RLA_TRY(up(dA + r0 * lda + k1, lda, ha + r0 * hrsa + k1, hrsa, rows, kr, pin_a));
+            if (cols) RLA_TRY(up(dB + k1 * ldb + c0, ldb, hb + k1 * hrsb + c0, hrsb, kr, cols, pin_b));
             cudaEvent_t ev_in = cx.events[3 * st], ev_row = cx.events[3 * st + 1], ev_col = cx.events[3 * st + 2];
             RLA_CUDA(cudaEventRecord(ev_in, cx.copy_in));
             // row strip: rows of panel st against every chunk uploaded so far (including this step's);
@@ -459,12 +505,12 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
             const size_t nrows_prev = (st < sm ? rb[st] : m);
             if (rows) {
                 RLA_CUDA(cudaStreamWaitEvent(cx.stream, ev_in, 0));
-                RLA_TRY(gemm_dev<T>(rows, k, ncols_avail, alpha, dA + r0 * lda, lda, dB, ldb, beta, dC + r0 * ldc, ldc, cx.stream));
+                RLA_TRY(tile_gemm(rows, ncols_avail, dA + r0 * lda, dB, dC + r0 * ldc, cx.stream));
                 RLA_CUDA(cudaEventRecord(ev_row, cx.stream));
             }
             if (cols && nrows_prev) {
                 RLA_CUDA(cudaStreamWaitEvent(cx.stream2, ev_in, 0));
-                RLA_TRY(gemm_dev<T>(nrows_prev, k, cols, alpha, dA, lda, dB + c0, ldb, beta, dC + c0, ldc, cx.stream2));
+                RLA_TRY(tile_gemm(nrows_prev, cols, dA, dB + c0, dC + c0, cx.stream2));
                 RLA_CUDA(cudaEventRecord(ev_col, cx.stream2));
             }
             if (rows) {
@@ -1136,6 +1182,16 @@ int rla_measure_peak(int kind, double *tflops) {
 
 int rla_set_tuning(const char *key, int value) {
     if (!key) return RLA_ERR_INVALID;
+    if (strcmp(key, "host_gemm_kprefix") == 0) {
+        if (value < -1 || value > 15) return RLA_ERR_INVALID;
+        g_host_gemm_kprefix = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "host_gemm_kchunk") == 0) {
+        if (value < 32 || value > 8192) return RLA_ERR_INVALID;
+        g_host_gemm_kchunk = value;
+        return RLA_OK;
+    }
     if (strcmp(key, "dgemm_streamk") == 0) {
         if (value < 0 || value > 3) return RLA_ERR_INVALID;
         g_dgemm_streamk = value;

@@ -64,9 +64,11 @@ struct DeviceOnce {
 int device_num_sms();            // lu.cu: SM count of the current device (cached per device)
 
 // ---- kernel launchers (one per .cu) ---------------------------------------------------------
+// acc_from_c: C <- alpha * (C + A*B) with the sum continued in the accumulators (beta ignored): consecutive k-chunks of one
+// product issued this way are bit-identical to the one-call product (dgemm.cu)
 int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda,
                  const double *b, size_t ldb, double beta, double *c, size_t ldc,
-                 cudaStream_t st);
+                 cudaStream_t st, bool acc_from_c = false);
 int sgemm_launch(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda,
                  const float *b, size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st);
 

@@ -131,7 +131,12 @@ __device__ __forceinline__ void mma_k4(double (&acc)[C::MT][C::NT][2], const dou
         for (int j = 0; j < C::NT; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
 }
 
-template <class C, bool ALIGNED>
+// ACC_C: the accumulators START from C instead of zero and the epilogue stores alpha * acc (C_out = alpha * (C_in + A*B),
+// beta is not used).  A product split along k into consecutive calls -- chunk 0 plain with alpha = 1, every later chunk
+// ACC_C, the last one with the caller's alpha -- then performs, per C element, exactly the DMMA accumulation chain of
+// the one-call product (chunk boundaries are multiples of 4), i.e. it is BIT-IDENTICAL to it.  The host pipeline uses
+// this to make work available linearly in the uploaded bytes during its first milliseconds (api.cu, gemm_host).
+template <class C, bool ALIGNED, bool ACC_C = false>
 __global__ void __launch_bounds__(C::THREADS, C::MINB)
 dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ A, size_t lda,
                   const double *__restrict__ B, size_t ldb, double beta, double *__restrict__ Cmat,
@@ -196,6 +201,29 @@ dgemm_dmma_kernel(int M, int N, int K, double alpha, const double *__restrict__ 
 
     const double *a_frag_base = As + (wm * C::MT * 8 + g) * C::LDAS + t;
     const double *b_frag_base = Bs + t * C::LDBS + wn * C::NT * 8 + g;
+
+    if (ACC_C) {                                 // (while the first slabs are in flight)
+        const bool vec_ok = ((ldc & 1) == 0) && ((reinterpret_cast<uintptr_t>(Cmat) & 15) == 0);
+#pragma unroll
+        for (int i = 0; i < C::MT; ++i) {
+            const int row = m0 + wm * C::MT * 8 + i * 8 + g;
+#pragma unroll
+            for (int j = 0; j < C::NT; ++j) {
+                const int col = n0 + wn * C::NT * 8 + j * 8 + 2 * t;
+                if (row < M && col < N) {
+                    const double *cp = Cmat + size_t(row) * ldc + col;
+                    if (col + 1 < N && vec_ok) {
+                        const double2 v = *reinterpret_cast<const double2 *>(cp);
+                        acc[i][j][0] = v.x;
+                        acc[i][j][1] = v.y;
+                    } else {
+                        acc[i][j][0] = cp[0];
+                        if (col + 1 < N) acc[i][j][1] = cp[1];
+                    }
+                }
+            }
+        }
+    }
 
     int stage = 0;
     for (int kt = 0; kt < KT; ++kt) {
@@ -491,7 +519,7 @@ __global__ void scale_c_kernel(size_t M, size_t N, T beta, T *C, size_t ldc) {
     *p = (beta == T(0)) ? T(0) : (*p) * beta;
 }
 
-template <class C, bool ALIGNED>
+template <class C, bool ALIGNED, bool ACC_C = false>
 int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
                double beta, double *c, size_t ldc, cudaStream_t st) {
     static DeviceOnce attr_once;
@@ -499,12 +527,12 @@ int launch_cfg(size_t m, size_t k, size_t n, double alpha, const double *a, size
     const size_t tiles = size_t(tiles_m) * tiles_n;
     if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
     if (const int od_ = attr_once.pending(); od_ >= 0) {
-        RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
-        RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+        RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED, ACC_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::SMEM)));
+        RLA_CUDA(cudaFuncSetAttribute(dgemm_dmma_kernel<C, ALIGNED, ACC_C>, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
         attr_once.done(od_);
     }
-    dgemm_dmma_kernel<C, ALIGNED><<<unsigned(tiles), C::THREADS, C::SMEM, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
-                                                                                beta, c, ldc, tiles_m, tiles_n);
+    dgemm_dmma_kernel<C, ALIGNED, ACC_C><<<unsigned(tiles), C::THREADS, C::SMEM, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb,
+                                                                                       beta, c, ldc, tiles_m, tiles_n);
     RLA_LAUNCHED();
     return RLA_OK;
 }
@@ -591,8 +619,21 @@ template int scale_c_launch<float>(size_t, size_t, float, float *, size_t, cudaS
 
 int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda,
                  const double *b, size_t ldb, double beta, double *c, size_t ldc,
-                 cudaStream_t st) {
+                 cudaStream_t st, bool acc_from_c) {
     if (m == 0 || n == 0) return RLA_OK;
+    if (acc_from_c) {
+        // C <- alpha * (C + A*B), the sum continued in the accumulators (see dgemm_dmma_kernel); aligned operands only
+        if (k == 0) return scale_c_launch<double>(m, n, alpha, c, ldc, st);
+        if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
+        if ((lda & 1) || (ldb & 1) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) return RLA_ERR_INVALID;
+        const double t128 = double((m + 127) / 128) * double((n + 127) / 128);
+        const double t64 = double((m + 63) / 64) * double((n + 63) / 64);
+        const double kd = double(k);
+        const double cost128 = ceil(t128 / 148.0) * 4.0 / (0.939 * kd / (kd + 28.0));
+        const double cost64 = ceil(t64 / 148.0) / (0.918 * kd / (kd + 8.0));
+        return cost128 < cost64 ? launch_cfg<CfgW16K32, true, true>(m, k, n, alpha, a, lda, b, ldb, 0.0, c, ldc, st)
+                                : launch_cfg<CfgTiny, true, true>(m, k, n, alpha, a, lda, b, ldb, 0.0, c, ldc, st);
+    }
     if (k == 0) return scale_c_launch<double>(m, n, beta, c, ldc, st);
     if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
     const bool aligned = ((lda & 1) == 0) && ((ldb & 1) == 0) &&

@@ -206,6 +206,20 @@ def test_gemm_host_2d_wavefront_pipeline(rla, oracle, dtype):
     assert not np.isnan(got2d).any()
     assert np.array_equal(got2d, got1d)
     check_gemm(oracle, a, b, got2d, positive=True)
+    if dtype == np.float64:
+        # k-prefix: the first quarter of k uploaded and multiplied as rank-512 / rank-256 updates of all of C that continue the
+        # accumulators (dgemm ACC_C), the wavefront on the rest: every element is still one accumulation chain => same bits
+        try:
+            for pre, kc in ((4, 512), (7, 256)):
+                assert l.rla_set_tuning(b"host_gemm_kprefix", pre) == 0 and l.rla_set_tuning(b"host_gemm_kchunk", kc) == 0
+                gotk = gpu_gemm_host(rla, a, b, alpha=-0.75)
+                assert l.rla_set_tuning(b"host_gemm_kprefix", 0) == 0
+                plain = gpu_gemm_host(rla, a, b, alpha=-0.75)
+                assert not np.isnan(gotk).any()
+                assert np.array_equal(gotk, plain), (pre, kc)
+        finally:
+            l.rla_set_tuning(b"host_gemm_kprefix", -1)
+            l.rla_set_tuning(b"host_gemm_kchunk", 256)
 
 
 @pytest.mark.parametrize("mode", [2, 3])
