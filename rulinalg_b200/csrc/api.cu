@@ -20,7 +20,7 @@ extern int g_sgemm_cfg;   // sgemm.cu
 extern int g_lu_gmax, g_lu_dbg, g_lu_cluster, g_lu_slab_rows;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 int g_host_gemm_s = 0;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline; 0 = auto (~512-row strips)
-int g_host_gemm_kprefix = -1;     // rla_set_tuning("host_gemm_kprefix", v): f64 2-D pipeline, fraction of k (in 1/16) uploaded and multiplied as
+int g_host_gemm_kprefix = -1;     // rla_set_tuning("host_gemm_kprefix", v): 2-D pipeline, fraction of k (in 1/16) uploaded and multiplied as
                                   // rank-kc updates of ALL of C before the wavefront starts; -1 = auto (k/4 when k >= 4096), 0 = off
 int g_host_gemm_kchunk = 256;     // rla_set_tuning("host_gemm_kchunk", kc): depth of those rank-kc updates (measured 256 / 512 / 1024: 35.7 / 36.1 / 37.2 ms)
 int g_host_gemm_grade = 0;        // rla_set_tuning("host_gemm_grade", 0/1): graded first / last strips of that pipeline (off: measured 37.9 vs 38.2 ms at 8192^3 pinned -- the start-up loss is the quadratic growth of computable work, not the strip size)
@@ -182,11 +182,15 @@ int gemm_dev<float>(size_t m, size_t k, size_t n, float alpha, const float *a, s
                     size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
     return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, beta, c, ldc, st);
 }
-// C <- alpha * (C + A*B), bit-identical continuation of a k-split product (f64 only: dgemm.cu ACC_C)
-template <typename T> constexpr bool gemm_has_acc() { return false; }
-template <> constexpr bool gemm_has_acc<double>() { return true; }
+// C <- alpha * (C + A*B), bit-identical continuation of a k-split product (dgemm.cu / sgemm.cu ACC_C)
+template <typename T> constexpr bool gemm_has_acc() { return true; }
 template <typename T>
-int gemm_dev_acc(size_t, size_t, size_t, T, const T *, size_t, const T *, size_t, T *, size_t, cudaStream_t) { return RLA_ERR_INVALID; }
+int gemm_dev_acc(size_t, size_t, size_t, T, const T *, size_t, const T *, size_t, T *, size_t, cudaStream_t);
+template <>
+int gemm_dev_acc<float>(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b, size_t ldb,
+                        float *c, size_t ldc, cudaStream_t st) {
+    return sgemm_launch(m, k, n, alpha, a, lda, b, ldb, 0.f, c, ldc, st, true);
+}
 template <>
 int gemm_dev_acc<double>(size_t m, size_t k, size_t n, double alpha, const double *a, size_t lda, const double *b, size_t ldb,
                          double *c, size_t ldc, cudaStream_t st) {
@@ -452,7 +456,7 @@ int gemm_host(size_t m, size_t k, size_t n, T alpha, const T *a, ptrdiff_t rsa, 
         boundaries(n, pn, cb);
         const size_t sm = rb.size() - 1, sn = cb.size() - 1;
         const size_t steps = sm > sn ? sm : sn;
-        // k-prefix (f64): the wavefront makes work available QUADRATICALLY in the uploaded bytes (a C tile needs a whole row
+        // k-prefix: the wavefront makes work available QUADRATICALLY in the uploaded bytes (a C tile needs a whole row
         // panel and a whole column chunk), which starves the GPU for the first ~6 ms at 8192^3.  Rank-kc updates of ALL of C
         // need only kc columns of A and kc rows of B each -- work LINEAR in the bytes -- so the first k1 = k/4 of the k
         // range is uploaded and multiplied that way (chunk 0 plain, later chunks continuing the accumulators: ACC_C), and the

@@ -70,7 +70,7 @@ int dgemm_launch(size_t m, size_t k, size_t n, double alpha, const double *a, si
                  const double *b, size_t ldb, double beta, double *c, size_t ldc,
                  cudaStream_t st, bool acc_from_c = false);
 int sgemm_launch(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda,
-                 const float *b, size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st);
+                 const float *b, size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st, bool acc_from_c = false);
 
 // LU workspace: owned by the per-thread context, grown on demand.
 struct LuWorkspace {

@@ -71,7 +71,10 @@ __device__ __forceinline__ void mma_frag(unsigned long long (&acc)[8][4], const 
     }
 }
 
-template <bool ALIGNED, int BM>
+// ACC_C: the accumulators start from C and the epilogue stores alpha * acc (C_out = alpha * (C_in + A*B)): consecutive k-chunks
+// of one product issued this way repeat, per element, the FMA chain of the one-call product bit for bit (see dgemm.cu; used by
+// the host pipeline's k-prefix).
+template <bool ALIGNED, int BM, bool ACC_C = false>
 __global__ void __launch_bounds__(2 * BM, BM == 128 ? 2 : 4)
 sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A, size_t lda,
                   const float *__restrict__ B, size_t ldb, float beta, float *__restrict__ C, size_t ldc,
@@ -173,6 +176,31 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
         load_a(0, r0, r1);
         copy_b(Bs, 0);
         cp_async_commit();
+        if (ACC_C) {
+            const bool cvec = ((ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(C) & 15) == 0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int row = m0 + ((i < 4) ? ty * 4 + i : HALF_M + ty * 4 + (i - 4));
+                if (row >= M) continue;
+                const float *crow = C + size_t(row) * ldc;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    const int col = n0 + h * 64 + tx * 4;
+                    if (col >= N) continue;
+                    float v[4] = {0.f, 0.f, 0.f, 0.f};
+                    if (col + 3 < N && cvec) {
+                        const float4 old = *reinterpret_cast<const float4 *>(crow + col);
+                        v[0] = old.x; v[1] = old.y; v[2] = old.z; v[3] = old.w;
+                    } else {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q)
+                            if (col + q < N) v[q] = crow[col + q];
+                    }
+                    acc[i][h * 2] = pack2(v[0], v[1]);
+                    acc[i][h * 2 + 1] = pack2(v[2], v[3]);
+                }
+            }
+        }
         store_a(As, r0, r1);
         cp_async_wait<0>();
         __syncthreads();
@@ -243,7 +271,7 @@ sgemm_ffma_kernel(int M, int N, int K, float alpha, const float *__restrict__ A,
 template <typename T>
 int scale_c_launch(size_t m, size_t n, T beta, T *c, size_t ldc, cudaStream_t st);
 
-template <bool ALIGNED, int BM>
+template <bool ALIGNED, int BM, bool ACC_C = false>
 int sgemm_launch_cfg(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b, size_t ldb,
                      float beta, float *c, size_t ldc, cudaStream_t st) {
     static DeviceOnce attr_once;
@@ -251,11 +279,11 @@ int sgemm_launch_cfg(size_t m, size_t k, size_t n, float alpha, const float *a, 
     const size_t tiles = size_t(tiles_m) * tiles_n;
     if (tiles > 0x7fffffffull) return RLA_ERR_INVALID;
     if (const int od_ = attr_once.pending(); od_ >= 0) {
-        RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<ALIGNED, BM>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
+        RLA_CUDA(cudaFuncSetAttribute(sgemm_ffma_kernel<ALIGNED, BM, ACC_C>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(SMEM_BYTES)));
         attr_once.done(od_);
     }
-    sgemm_ffma_kernel<ALIGNED, BM><<<unsigned(tiles), 2 * BM, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb, beta, c,
-                                                                                ldc, tiles_m, tiles_n);
+    sgemm_ffma_kernel<ALIGNED, BM, ACC_C><<<unsigned(tiles), 2 * BM, SMEM_BYTES, st>>>(int(m), int(n), int(k), alpha, a, lda, b, ldb, beta,
+                                                                                       c, ldc, tiles_m, tiles_n);
     RLA_LAUNCHED();
     return RLA_OK;
 }
@@ -263,8 +291,16 @@ int sgemm_launch_cfg(size_t m, size_t k, size_t n, float alpha, const float *a, 
 int g_sgemm_cfg = -1;    // rla_set_tuning("sgemm_cfg", v): -1 auto, 0 = 128 x 128 tiles, 1 = 64 x 128 tiles
 
 int sgemm_launch(size_t m, size_t k, size_t n, float alpha, const float *a, size_t lda, const float *b,
-                 size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st) {
+                 size_t ldb, float beta, float *c, size_t ldc, cudaStream_t st, bool acc_from_c) {
     if (m == 0 || n == 0) return RLA_OK;
+    if (acc_from_c) {
+        if (k == 0) return scale_c_launch<float>(m, n, alpha, c, ldc, st);
+        if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
+        if ((lda & 3) || (ldb & 3) || (reinterpret_cast<uintptr_t>(a) & 15) || (reinterpret_cast<uintptr_t>(b) & 15)) return RLA_ERR_INVALID;
+        const size_t t128 = ((m + 127) / 128) * ((n + 127) / 128);
+        return t128 * 10 < size_t(device_num_sms()) * 9 ? sgemm_launch_cfg<true, 64, true>(m, k, n, alpha, a, lda, b, ldb, 0.f, c, ldc, st)
+                                                          : sgemm_launch_cfg<true, 128, true>(m, k, n, alpha, a, lda, b, ldb, 0.f, c, ldc, st);
+    }
     if (k == 0) return scale_c_launch<float>(m, n, beta, c, ldc, st);
     if (m > 0x7fffffffull || n > 0x7fffffffull || k > 0x7fffffffull) return RLA_ERR_INVALID;
     const bool aligned = ((lda & 3) == 0) && ((ldb & 3) == 0) && ((reinterpret_cast<uintptr_t>(a) & 15) == 0) &&

@@ -206,9 +206,9 @@ def test_gemm_host_2d_wavefront_pipeline(rla, oracle, dtype):
     assert not np.isnan(got2d).any()
     assert np.array_equal(got2d, got1d)
     check_gemm(oracle, a, b, got2d, positive=True)
-    if dtype == np.float64:
-        # k-prefix: the first quarter of k uploaded and multiplied as rank-512 / rank-256 updates of all of C that continue the
-        # accumulators (dgemm ACC_C), the wavefront on the rest: every element is still one accumulation chain => same bits
+    if True:
+        # k-prefix: the first part of k uploaded and multiplied as rank-512 / rank-256 updates of all of C that continue the
+        # accumulators (dgemm / sgemm ACC_C), the wavefront on the rest: every element is still one accumulation chain => same bits
         try:
             for pre, kc in ((4, 512), (7, 256)):
                 assert l.rla_set_tuning(b"host_gemm_kprefix", pre) == 0 and l.rla_set_tuning(b"host_gemm_kchunk", kc) == 0
