@@ -94,3 +94,57 @@ def test_held_operand_skips_the_upload(rla, oracle):
     assert np.array_equal(c_plain, c_held)
     print(f"thin product with B pageable: {t_plain * 1e3:.2f} ms, with B held: {t_held * 1e3:.2f} ms")
     assert t_held < 0.6 * t_plain
+
+
+def test_held_matrix_in_solves_and_matvec(rla, oracle):
+    """The matrix operand of rla_dgetrs / rla_dtrsv / rla_dgemv is served from HBM while its host range is held: for these
+    O(n^2)-flop calls the upload is the whole cost (lu.rs:203-206: "multiple such linear systems involving the same A")."""
+    import ctypes as C
+    l = rla.lib()
+    n = 3000
+    a = oracle.fill_uniform((n, n), 21, np.float64) + n * np.eye(n)
+    lu = a.copy()
+    perm = np.zeros(n, dtype=np.uint64)
+    assert l.rla_dgetrf(n, lu.ctypes.data, perm.ctypes.data) == 0
+    rhs = [oracle.fill_uniform((n,), 40 + i, np.float64) for i in range(3)]
+
+    def solve(b):
+        x = b.copy()
+        assert l.rla_dgetrs(n, lu.ctypes.data, perm.ctypes.data, x.ctypes.data) == 0
+        return x
+
+    def timed(fn, *args):
+        t0 = time.perf_counter(); out = fn(*args); return out, time.perf_counter() - t0
+
+    plain = [solve(b) for b in rhs]
+    _, t_plain = timed(solve, rhs[0])
+    assert l.rla_operand_resident_bytes() == 0
+    assert l.rla_operand_hold(lu.ctypes.data, lu.nbytes) == 0
+    try:
+        first = solve(rhs[0])                                   # uploads and keeps the factors
+        assert l.rla_operand_resident_bytes() >= lu.nbytes
+        held = [solve(b) for b in rhs]
+        _, t_held = timed(solve, rhs[0])
+        assert np.array_equal(first, plain[0])
+        for p_, h_ in zip(plain, held):
+            assert np.array_equal(p_, h_)
+        # the same held matrix as a triangle and in a matrix-vector product
+        xt = rhs[1].copy(); xt2 = rhs[1].copy()
+        assert l.rla_dtrsv(0, n, lu.ctypes.data, n, xt.ctypes.data) == 0
+        y = np.empty(n); y2 = np.empty(n)
+        assert l.rla_dgemv(n, n, lu.ctypes.data, n, rhs[2].ctypes.data, y.ctypes.data) == 0
+        kept = l.rla_operand_resident_bytes()
+        assert l.rla_dtrsv(0, n, lu.ctypes.data, n, xt2.ctypes.data) == 0
+        assert l.rla_dgemv(n, n, lu.ctypes.data, n, rhs[2].ctypes.data, y2.ctypes.data) == 0
+        assert l.rla_operand_resident_bytes() == kept == first.nbytes * 0 + kept
+    finally:
+        assert l.rla_operand_release(lu.ctypes.data) == 0
+    assert l.rla_operand_resident_bytes() == 0
+    xt_plain = rhs[1].copy()
+    assert l.rla_dtrsv(0, n, lu.ctypes.data, n, xt_plain.ctypes.data) == 0
+    y_plain = np.empty(n)
+    assert l.rla_dgemv(n, n, lu.ctypes.data, n, rhs[2].ctypes.data, y_plain.ctypes.data) == 0
+    assert np.array_equal(xt, xt_plain) and np.array_equal(xt2, xt_plain)
+    assert np.array_equal(y, y_plain) and np.array_equal(y2, y_plain)
+    print(f"solve n={n}: factors re-uploaded {t_plain * 1e3:.2f} ms, held {t_held * 1e3:.2f} ms")
+    assert t_held < 0.6 * t_plain
