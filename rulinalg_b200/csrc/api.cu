@@ -684,8 +684,27 @@ int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm,
         int32_t *hInfo = static_cast<int32_t *>(cx.hSmall.p);
         Stager &stg = cx.stager;
         const bool pinned = !g_host_stage || host_is_pinned(lu);
-        RLA_TRY(stg.upload2d(dA, ld * sizeof(T), lu, n * sizeof(T), n * sizeof(T), n, pinned, cx.device, cx.stream));
         size_t nev = 0;
+        // The first outer block's factorisation reads nothing but the first 256 columns: they go up first, the rest of the
+        // matrix follows on the copy stream UNDER that block's panel kernels (n = 4096: 0.6 of the 2.4 ms upload hidden).
+        const size_t w0 = 256;
+        const bool split_up = n >= 2048;
+        cudaEvent_t e_first = nullptr, e_rest = nullptr;
+        if (split_up) {
+            RLA_TRY(cx.event(nev++, &e_first));
+            RLA_TRY(cx.event(nev++, &e_rest));
+            RLA_TRY(stg.upload2d(dA, ld * sizeof(T), lu, n * sizeof(T), w0 * sizeof(T), n, pinned, cx.device, cx.copy_in));
+            RLA_CUDA(cudaEventRecord(e_first, cx.copy_in));
+            RLA_TRY(stg.upload2d(dA + w0, ld * sizeof(T), lu + w0, n * sizeof(T), (n - w0) * sizeof(T), n, pinned, cx.device, cx.copy_in));
+            RLA_CUDA(cudaEventRecord(e_rest, cx.copy_in));
+            RLA_CUDA(cudaStreamWaitEvent(cx.stream, e_first, 0));
+        } else {
+            RLA_TRY(stg.upload2d(dA, ld * sizeof(T), lu, n * sizeof(T), n * sizeof(T), n, pinned, cx.device, cx.stream));
+        }
+        LuAfterFirstBlock after_first = [&](cudaStream_t st) -> int {
+            RLA_CUDA(cudaStreamWaitEvent(st, e_rest, 0));
+            return RLA_OK;
+        };
         const bool overlap = n >= 1024;            // below that one download after the factorisation is just as fast
         LuRowsFinal rows_final = [&](int row0, int nrows, cudaStream_t st) -> int {
             cudaEvent_t e;
@@ -695,7 +714,7 @@ int getrf_host(size_t n, T *lu, size_t *perm, T **keep_dev, int64_t **keep_perm,
             return stg.download2d(lu + size_t(row0) * n, n * sizeof(T), dA + size_t(row0) * ld, ld * sizeof(T), n * sizeof(T),
                                   size_t(nrows), pinned, cx.device, cx.copy_out);
         };
-        RLA_TRY(getrf_launch<T>(n, dA, ld, dP, dInfo, cx.lu_ws, cx.stream, overlap ? &rows_final : nullptr));
+        RLA_TRY(getrf_launch<T>(n, dA, ld, dP, dInfo, cx.lu_ws, cx.stream, overlap ? &rows_final : nullptr, split_up ? &after_first : nullptr));
         RLA_CUDA(cudaMemcpyAsync(hInfo, dInfo, sizeof(int32_t), cudaMemcpyDeviceToHost, cx.stream));
         static_assert(sizeof(size_t) == sizeof(int64_t), "LP64 expected");
         RLA_CUDA(cudaMemcpyAsync(perm, dP, n * sizeof(int64_t), cudaMemcpyDeviceToHost, cx.stream));

@@ -86,9 +86,13 @@ struct LuWorkspace {
 // optional hook of getrf_launch: called (at enqueue time) when rows [row0, row0 + nrows) of the packed factors can no
 // longer change -- everything queued on `st` so far produces them; the host API starts their download there
 using LuRowsFinal = std::function<int(int row0, int nrows, cudaStream_t st)>;
+// optional hook of getrf_launch: called once, right after the first outer block's factorisation has been enqueued -- the
+// only part of the algorithm that touches nothing but the first 256 columns; the host API makes `st` wait there for the
+// upload of the remaining columns, which so runs under that block's panel kernels
+using LuAfterFirstBlock = std::function<int(cudaStream_t st)>;
 template <typename T>
 int getrf_launch(size_t n, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws,
-                 cudaStream_t st, const LuRowsFinal *rows_final = nullptr);
+                 cudaStream_t st, const LuRowsFinal *rows_final = nullptr, const LuAfterFirstBlock *after_first = nullptr);
 template <typename T>
 int getrs_launch(size_t n, const T *lu, size_t ld, const int64_t *d_perm, T *d_b, T *ws3,
                  int32_t *d_info, int32_t *d_flags, cudaStream_t st);

@@ -2431,7 +2431,7 @@ int lu_trace_fetch(unsigned long long *host512) {
 
 template <typename T>
 int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, LuWorkspace &ws, cudaStream_t st,
-                 const LuRowsFinal *rows_final) {
+                 const LuRowsFinal *rows_final, const LuAfterFirstBlock *after_first) {
     if (n_ > lu_max_n(sizeof(T))) return RLA_ERR_INVALID;      // checked up front: nothing has been enqueued yet
     const int n = int(n_);
     RLA_CUDA(cudaMemsetAsync(d_info, 0, sizeof(int32_t), st));
@@ -2462,6 +2462,7 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
         RLA_CUDA(cudaEventCreateWithFlags(&ws.ev_fact, cudaEventDisableTiming));
     }
     RLA_TRY(factor_block<T>(ws, a, ld, n, 0, min(OUTER_W, n), ipiv, d_info, plan, st));
+    if (after_first) RLA_TRY((*after_first)(st));
     for (int J0 = 0; J0 < n; J0 += OUTER_W) {
         const int w = min(OUTER_W, n - J0);
         // interchanges of the whole outer block applied left and right of it, and to the row-origin vector
@@ -2495,8 +2496,8 @@ int getrf_launch(size_t n_, T *a, size_t ld, int64_t *d_perm, int32_t *d_info, L
     return RLA_OK;
 }
 
-template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t, const LuRowsFinal *);
-template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t, const LuRowsFinal *);
+template int getrf_launch<double>(size_t, double *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t, const LuRowsFinal *, const LuAfterFirstBlock *);
+template int getrf_launch<float>(size_t, float *, size_t, int64_t *, int32_t *, LuWorkspace &, cudaStream_t, const LuRowsFinal *, const LuAfterFirstBlock *);
 
 // PartialPivLu::inverse (lu.rs:251-285) as a blocked multi-RHS solve: X = U^-1 L^-1 P with all n unit vectors at once
 // (SURVEY 8f rank 1).  The reference performs n separate solves; this is 2n^3 flops on the GEMM kernels instead.
