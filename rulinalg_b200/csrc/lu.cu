@@ -175,7 +175,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
     if (*info != 0) return;   // an earlier panel hit a tiny pivot: written by a previous kernel => uniform
     extern __shared__ __align__(16) unsigned char panel_smem[];
     T *s = reinterpret_cast<T *>(panel_smem);
-    __shared__ T prow_s[PW];
+    __shared__ T prow_s[2][PW];                    // pivot rows of the current and the previous column (deferred update)
     __shared__ unsigned long long red_key[2][PANEL_THREADS / 32];
     __shared__ int red_idx[2][PANEL_THREADS / 32];
     __shared__ T sh_abs;
@@ -291,13 +291,21 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
     }
     __syncthreads();
 
+    // The rank-1 update of column c is DEFERRED: only column c+1 is brought up to date before the next pivot search
+    // (it is all the search needs); the update of columns c+2.. runs in the next iteration, under the grid-wide exchange
+    // of the candidates -- first the two rows that have to be published (the CTA's candidate row and the diagonal row),
+    // then everything else by warps 1..15 while warp 0 polls the packets.  For tall panels the update is shared-memory
+    // bound (n = 32768: 393 rows x 63 columns per CTA, ~0.8 us per column) and used to sit between two exchanges; now
+    // a column costs max(exchange, update) instead of their sum.  Every element still receives the same single
+    // a - m*u per column, in ascending column order => bit-identical to the other panel kernels (asserted).
     for (int c = 0; c < jb; ++c) {
         const int d = J + c;                       // global diagonal row of this column
         const int par = c & 1;
         const unsigned tag = tag_base + unsigned(c) + 1u;
         const unsigned long long tag_hi = (unsigned long long)tag << 32;   // (pivot log: 8-byte entries, atomic as they are)
-        const int lo = max(0, d - r0);             // first local row still active
+        const int lo = max(0, d - r0);             // first local row still active (== first row the deferred update touches)
         const bool owns_d = (d >= r0 && d < r1);
+        const T *pu = prow_s[(c + 1) & 1];         // pivot row of column c-1 (deferred update)
 
         if (b == 0) TRACE(0);
         // ---- local argmax over active rows of column c (first max wins) ----
@@ -313,46 +321,55 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             unsigned wm;
             warp_argmax(bkey, bidx, wm);
         }
-        if (lane == 0) { red_key[0][warp] = bkey; red_idx[0][warp] = bidx; }
+        if (lane == 0) { red_key[par][warp] = bkey; red_idx[par][warp] = bidx; }
         __syncthreads();
-        if (warp == 0) {
-            bkey = (lane < PANEL_THREADS / 32) ? red_key[0][lane] : 0ull;
-            bidx = (lane < PANEL_THREADS / 32) ? red_idx[0][lane] : INT_MAX;
+        // every warp reduces the 16 warp candidates itself (one CTA barrier instead of two; the buffers alternate by column)
+        bkey = (lane < PANEL_THREADS / 32) ? red_key[par][lane] : 0ull;
+        bidx = (lane < PANEL_THREADS / 32) ? red_idx[par][lane] : INT_MAX;
+        {
             unsigned wm;
             warp_argmax(bkey, bidx, wm);
-            if (lane == 0) {
-                // reference starts the scan with curr_max = a_dd even when it is NaN (lu.rs:170-171):
-                // then no later row can win.  Post +inf for that row so it wins the global reduce.
-                if (owns_d) {
-                    const T dv = s[(d - r0) * PLDS + c];
-                    if (dv != dv) { bkey = key_of(CUDART_INF); bidx = d; }
-                }
-                sh_idx = bidx;
-                // candidate packet first: it is what the hub is waiting for
-                packet_store(sc.packets + par * GMAX + b, bkey, bidx, tag);
-                if (b == 0 && sc.trace) sc.trace[c * 8 + 1] = gtime();
+        }
+        // reference starts the scan with curr_max = a_dd even when it is NaN (lu.rs:170-171):
+        // then no later row can win.  Post +inf for that row so it wins the global reduce.
+        if (owns_d) {
+            const T dv = s[(d - r0) * PLDS + c];
+            if (dv != dv) { bkey = key_of(CUDART_INF); bidx = d; }
+        }
+        if (tid == 0) {
+            // candidate packet first: it is what everybody is waiting for
+            packet_store(sc.packets + par * GMAX + b, bkey, bidx, tag);
+            if (b == 0 && sc.trace) sc.trace[c * 8 + 1] = gtime();
+        }
+        // ---- candidate row (and the diagonal row) as self-validating chunks; their deferred update comes first ----
+        const int li = bidx;
+        const int li_loc = (li != INT_MAX) ? li - r0 : -1;
+        {
+            if (li != INT_MAX && tid < jb) {
+                T v = s[li_loc * PLDS + tid];
+                if (c > 0 && tid > c) { v = sub_rn(v, mul_rn(s[li_loc * PLDS + c - 1], pu[tid])); s[li_loc * PLDS + tid] = v; }
+                chunk_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(v), tag);
+                if (li == d) chunk_store(sc.diagbuf + par * PW + tid, bits_of(v), tag);     // the candidate IS the diagonal row
+            }
+            if (owns_d && li != d && tid >= 64 && tid < 64 + jb) {
+                const int cc = tid - 64, dl = d - r0;
+                T v = s[dl * PLDS + cc];
+                if (c > 0 && cc > c) { v = sub_rn(v, mul_rn(s[dl * PLDS + c - 1], pu[cc])); s[dl * PLDS + cc] = v; }
+                chunk_store(sc.diagbuf + par * PW + cc, bits_of(v), tag);
             }
         }
-        __syncthreads();
-        // ---- candidate row (and the diagonal row) as self-validating chunks ----
-        {
-            const int li = sh_idx;
-            if (li != INT_MAX && tid < jb)
-                chunk_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(s[(li - r0) * PLDS + tid]), tag);
-            if (owns_d && tid >= 64 && tid < 64 + jb)
-                chunk_store(sc.diagbuf + par * PW + (tid - 64), bits_of(s[(d - r0) * PLDS + (tid - 64)]), tag);
-        }
         // ---- the verdict: every row CTA reads the G candidate packets itself with ONE whole warp (ceil(G/32)
-        //      packets per lane; lanes past G duplicate packet G-1 so the warp is never partially active) ----
+        //      packets per lane; lanes past G duplicate packet G-1 so the warp is never partially active); the other
+        //      15 warps meanwhile finish the deferred update of column c-1 on all other rows ----
         if (warp == 0) {
             unsigned long long gk = 0ull;
             int gi = INT_MAX, gw = 0;
             for (int base = 0; base < G; base += 32) {
                 const int q = min(base + lane, G - 1);
-                unsigned long long lo;
+                unsigned long long lo_;
                 int i1;
-                while (!packet_load(sc.packets + par * GMAX + q, tag, lo, i1)) {}
-                if (lo > gk || (lo == gk && i1 < gi)) { gk = lo; gi = i1; gw = q; }
+                while (!packet_load(sc.packets + par * GMAX + q, tag, lo_, i1)) {}
+                if (lo_ > gk || (lo_ == gk && i1 < gi)) { gk = lo_; gi = i1; gw = q; }
             }
             unsigned wm;
             warp_argmax(gk, gi, wm);
@@ -369,54 +386,69 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
                     if (sc.trace) sc.trace[c * 8 + 7] = (unsigned long long)(unsigned)gi;
                 }
             }
+        } else if (c > 0 && c + 1 < jb) {
+            // rows [lo, nrows) except the two handled above, columns c+1.. : four rows in flight per warp
+            constexpr int NW = PANEL_THREADS / 32 - 1;
+            const int dl = owns_d ? d - r0 : -1;
+            for (int rb = lo + (warp - 1); rb < nrows; rb += 4 * NW) {
+                T m[4];
+                bool on[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int r = rb + u * NW;
+                    on[u] = r < nrows && r != li_loc && r != dl;
+                    m[u] = on[u] ? s[r * PLDS + c - 1] : T(0);
+                }
+                for (int cc = c + 1 + lane; cc < jb; cc += 32) {
+                    const T pv = pu[cc];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int r = rb + u * NW;
+                        if (on[u]) s[r * PLDS + cc] = sub_rn(s[r * PLDS + cc], mul_rn(m[u], pv));
+                    }
+                }
+            }
         }
         __syncthreads();
         if (b == 0) TRACE(2);
         const int prow_idx = sh_idx, win = sh_win;
         if (sh_sing) return;                       // uniform across the grid (every CTA reduces the same packets)
+        T *prow_c = prow_s[par];
+        // the pivot row arrives (warps 0-1) and, if rows d <-> prow_idx swap inside the panel, goes straight into row d
+        // while warps 2-3 bring the old diagonal row into row prow_idx: one phase, one barrier
         if ((tid & ~31) < jb) {                   // whole warps poll (lanes past jb re-read chunk jb-1)
             unsigned long long vlo;
             const Msg *src = sc.rowbuf + size_t(par * GMAX + win) * PW + min(tid, jb - 1);
             while (!chunk_load(src, tag, vlo)) {}
             T v;
             from_bits(vlo, v);
-            if (tid < jb) prow_s[tid] = v;
+            if (tid < jb) {
+                prow_c[tid] = v;
+                if (prow_idx != d && owns_d) s[(d - r0) * PLDS + tid] = v;
+            }
+        } else if (prow_idx != d && prow_idx >= r0 && prow_idx < r1 && tid >= 64 && ((tid - 64) & ~31) < jb) {
+            unsigned long long vlo;
+            const Msg *src = sc.diagbuf + par * PW + min(tid - 64, jb - 1);
+            while (!chunk_load(src, tag, vlo)) {}
+            T v;
+            from_bits(vlo, v);
+            if (tid - 64 < jb) s[(prow_idx - r0) * PLDS + (tid - 64)] = v;
         }
         __syncthreads();
-        if (prow_idx != d) {                       // swap rows d <-> prow_idx inside the panel
-            if (owns_d && tid < jb) s[(d - r0) * PLDS + tid] = prow_s[tid];
-            if (prow_idx >= r0 && prow_idx < r1 && tid >= 64 && ((tid - 64) & ~31) < jb) {
-                unsigned long long vlo;
-                const Msg *src = sc.diagbuf + par * PW + min(tid - 64, jb - 1);
-                while (!chunk_load(src, tag, vlo)) {}
-                T v;
-                from_bits(vlo, v);
-                if (tid - 64 < jb) s[(prow_idx - r0) * PLDS + (tid - 64)] = v;
-            }
-            __syncthreads();
-        }
         if (b == 0) TRACE(3);
-        // ---- multipliers (one IEEE division per row), then rank-1 update with mul, sub ----
-        const T piv = prow_s[c];
+        // ---- multipliers (one IEEE division per row) and column c+1 (mul, sub) -- all the next pivot search needs;
+        //      the rest of this column's rank-1 update is deferred into the next iteration ----
+        const T piv = prow_c[c];
         const int lo2 = max(0, d + 1 - r0);
-        for (int r = lo2 + tid; r < nrows; r += PANEL_THREADS) s[r * PLDS + c] = div_rn(s[r * PLDS + c], piv);
-        __syncthreads();
         if (c + 1 < jb) {
-            // rank-1 update, four rows in flight per warp (independent mul/sub chains)
-            constexpr int NW = PANEL_THREADS / 32;
-            for (int rb = lo2 + warp; rb < nrows; rb += 4 * NW) {
-                T m[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) m[u] = (rb + u * NW < nrows) ? s[(rb + u * NW) * PLDS + c] : T(0);
-                for (int cc = c + 1 + lane; cc < jb; cc += 32) {
-                    const T pv = prow_s[cc];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int r = rb + u * NW;
-                        if (r < nrows) s[r * PLDS + cc] = sub_rn(s[r * PLDS + cc], mul_rn(m[u], pv));
-                    }
-                }
+            const T pn = prow_c[c + 1];
+            for (int r = lo2 + tid; r < nrows; r += PANEL_THREADS) {
+                const T m = div_rn(s[r * PLDS + c], piv);
+                s[r * PLDS + c] = m;
+                s[r * PLDS + c + 1] = sub_rn(s[r * PLDS + c + 1], mul_rn(m, pn));
             }
+        } else {
+            for (int r = lo2 + tid; r < nrows; r += PANEL_THREADS) s[r * PLDS + c] = div_rn(s[r * PLDS + c], piv);
         }
         __syncthreads();
         if (b == 0) TRACE(4);

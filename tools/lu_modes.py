@@ -11,7 +11,7 @@ for n in sizes:
     rla.check(l.rla_fill_uniform_f64_dev(a0.data_ptr(), n, n, n, 12, 0, 0.0, 1.0, s))
     a = torch.empty_like(a0)
     perm = torch.empty(n, dtype=torch.int64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
-    for mode in (0, 1, 2):
+    for mode in (0, 1):
         rla.check(l.rla_set_tuning(b"lu_cluster", mode))
         best = 1e30
         for _ in range(4):
