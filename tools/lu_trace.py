@@ -6,6 +6,7 @@ import rulinalg_b200 as rla
 l = rla.lib(); rla.check(l.rla_init(0))
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 l.rla_set_tuning(b"lu_dbg", 8 | 4)
+if len(sys.argv) > 2: l.rla_set_tuning(b"lu_cluster", int(sys.argv[2]))
 s = torch.cuda.current_stream().cuda_stream
 a = torch.rand(n, n, dtype=torch.float64, device="cuda")
 perm = torch.empty(n, dtype=torch.int64, device="cuda"); info = torch.zeros(1, dtype=torch.int32, device="cuda")
