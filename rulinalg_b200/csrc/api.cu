@@ -17,7 +17,7 @@ namespace rla {
 
 extern int g_dgemm_cfg, g_dgemm_streamk;   // dgemm.cu
 extern int g_sgemm_cfg;   // sgemm.cu
-extern int g_lu_gmax, g_lu_dbg, g_lu_cluster, g_lu_slab_rows;   // lu.cu
+extern int g_lu_gmax, g_lu_dbg, g_lu_cluster, g_lu_slab_rows, g_lu_k3e_rows;   // lu.cu
 int g_host_gemm_2d = 1;           // rla_set_tuning("host_gemm_2d", 0/1): 2-D wavefront host pipeline on/off
 int g_host_gemm_s = 0;            // rla_set_tuning("host_gemm_s", S): panels/chunks per dimension of that pipeline; 0 = auto (~512-row strips)
 int g_host_gemm_kprefix = -1;     // rla_set_tuning("host_gemm_kprefix", v): 2-D pipeline, fraction of k (in 1/16) uploaded and multiplied as
@@ -1298,8 +1298,13 @@ int rla_set_tuning(const char *key, int value) {
         return RLA_OK;
     }
     if (strcmp(key, "lu_cluster") == 0) {
-        if (value < 0 || value > 4) return RLA_ERR_INVALID;
+        if (value < 0 || value > 5) return RLA_ERR_INVALID;
         g_lu_cluster = value;
+        return RLA_OK;
+    }
+    if (strcmp(key, "lu_k3e_rows") == 0) {
+        if (value < 0) return RLA_ERR_INVALID;
+        g_lu_k3e_rows = value;
         return RLA_OK;
     }
     if (strcmp(key, "lu_slab_rows") == 0) {

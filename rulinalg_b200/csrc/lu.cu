@@ -165,10 +165,70 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 #define TRACE(slot) do { if (sc.trace && tid == 0) sc.trace[c * 8 + (slot)] = gtime(); } while (0)
+// ---- thread-block-cluster / DSMEM primitives (used by the cluster variants of the panel kernels) ----
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
+__device__ __forceinline__ unsigned cluster_ctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+    unsigned r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
+    unsigned r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
+}
+// remote 16-byte store that completes 16 tx-bytes on the destination CTA's mbarrier when the data has landed
+__device__ __forceinline__ void st_async_v2(unsigned cluster_addr, unsigned long long lo, unsigned long long hi,
+                                            unsigned cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+                 "l"(lo), "l"(hi), "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned addr, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ double ld_cluster(const double *p, unsigned rank) {
+    unsigned long long v;
+    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(mapa(smem_u32(p), rank)) : "memory");
+    return __longlong_as_double((long long)v);
+}
+__device__ __forceinline__ float ld_cluster(const float *p, unsigned rank) {
+    unsigned v;
+    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(mapa(smem_u32(p), rank)) : "memory");
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
+}
 constexpr int HUB_PLAN_WARP = 5;                  // hub warp 0 follows the pivot log, warp 5 maintains the plan
 constexpr int HUB_SWAP_T0 = 192;                  // warps 6..15 apply the interchanges
 
-template <typename T>
+// CL (cluster mode, panels whose rows fit ONE thread-block cluster of G <= 16 CTAs): the same kernel with the exchange over the
+// SM-to-SM network instead of L2 -- the candidate packets go to every CTA with st.async + mbarrier complete_tx, the CTA's
+// candidate row (and the diagonal row) are staged in ITS shared memory before the packet leaves, and the winner's row is
+// pulled with ld.shared::cluster after the verdict.  Launched as two clusters: CTAs 0..G-1 hold the rows, CTA G is the hub,
+// CTAs G+1.. exit.  Everything else (deferred update, arithmetic, pivot rule) is shared with the L2 path => bit-identical.
+template <typename T, bool CL>
 __global__ void __launch_bounds__(PANEL_THREADS, 1)
 lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G, int32_t *__restrict__ ipiv,
                 int32_t *__restrict__ info, PanelScratch sc, unsigned tag_base, int J0, int w, int dbg) {
@@ -181,9 +241,14 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
     __shared__ T sh_abs;
     __shared__ int sh_idx, sh_win, sh_sing;
     __shared__ int piv_sm[PW];
+    __shared__ __align__(16) Msg cl_cand[2][16];           // CL: [parity][source rank], written remotely (st.async)
+    __shared__ __align__(8) unsigned long long cl_bar[2];  // CL: one mbarrier per parity (1 arrival + 16*G tx-bytes)
+    __shared__ __align__(16) T cl_crow[2][PW];             // CL: my candidate row, staged for remote readers
+    __shared__ __align__(16) T cl_drow[2][PW];             // CL: the diagonal row (its owner's copy)
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
+    if (CL && b > G) return;                               // the hub's cluster: only its first CTA works
 
     if (b >= G) {
         // =========================== hub CTA ===========================
@@ -285,11 +350,19 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
     const int r1 = min(n, r0 + R);
     const int nrows = max(0, r1 - r0);
 
+    if (CL) {
+        if (tid == 0) {
+            mbar_init(smem_u32(&cl_bar[0]), 1);
+            mbar_init(smem_u32(&cl_bar[1]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+    }
     for (int idx = tid; idx < nrows * jb; idx += PANEL_THREADS) {
         const int r = idx / jb, c = idx - r * jb;
         s[r * PLDS + c] = A[size_t(r0 + r) * ld + J + c];
     }
     __syncthreads();
+    if (CL) cluster_sync_all();                            // every CTA's mbarriers are initialised before any packet travels
 
     // The rank-1 update of column c is DEFERRED: only column c+1 is brought up to date before the next pivot search
     // (it is all the search needs); the update of columns c+2.. runs in the next iteration, under the grid-wide exchange
@@ -336,7 +409,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             const T dv = s[(d - r0) * PLDS + c];
             if (dv != dv) { bkey = key_of(CUDART_INF); bidx = d; }
         }
-        if (tid == 0) {
+        if (!CL && tid == 0) {
             // candidate packet first: it is what everybody is waiting for
             packet_store(sc.packets + par * GMAX + b, bkey, bidx, tag);
             if (b == 0 && sc.trace) sc.trace[c * 8 + 1] = gtime();
@@ -348,22 +421,43 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
             if (li != INT_MAX && tid < jb) {
                 T v = s[li_loc * PLDS + tid];
                 if (c > 0 && tid > c) { v = sub_rn(v, mul_rn(s[li_loc * PLDS + c - 1], pu[tid])); s[li_loc * PLDS + tid] = v; }
-                chunk_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(v), tag);
-                if (li == d) chunk_store(sc.diagbuf + par * PW + tid, bits_of(v), tag);     // the candidate IS the diagonal row
+                if (CL) {
+                    cl_crow[par][tid] = v;
+                    if (li == d) cl_drow[par][tid] = v;
+                } else {
+                    chunk_store(sc.rowbuf + size_t(par * GMAX + b) * PW + tid, bits_of(v), tag);
+                    if (li == d) chunk_store(sc.diagbuf + par * PW + tid, bits_of(v), tag);     // the candidate IS the diagonal row
+                }
             }
             if (owns_d && li != d && tid >= 64 && tid < 64 + jb) {
                 const int cc = tid - 64, dl = d - r0;
                 T v = s[dl * PLDS + cc];
                 if (c > 0 && cc > c) { v = sub_rn(v, mul_rn(s[dl * PLDS + c - 1], pu[cc])); s[dl * PLDS + cc] = v; }
-                chunk_store(sc.diagbuf + par * PW + cc, bits_of(v), tag);
+                if (CL) cl_drow[par][cc] = v;
+                else chunk_store(sc.diagbuf + par * PW + cc, bits_of(v), tag);
             }
         }
+        if (CL) __syncthreads();                           // the rows are in shared memory BEFORE the packet that announces them leaves
         // ---- the verdict: every row CTA reads the G candidate packets itself with ONE whole warp (ceil(G/32)
         //      packets per lane; lanes past G duplicate packet G-1 so the warp is never partially active); the other
         //      15 warps meanwhile finish the deferred update of column c-1 on all other rows ----
         if (warp == 0) {
             unsigned long long gk = 0ull;
             int gi = INT_MAX, gw = 0;
+            if (CL) {
+                if (lane == 0) mbar_expect_tx(smem_u32(&cl_bar[par]), 16u * unsigned(G));
+                __syncwarp();
+                if (lane < G)
+                    st_async_v2(mapa(smem_u32(&cl_cand[par][b]), unsigned(lane)), bkey, (unsigned long long)(unsigned)bidx,
+                                mapa(smem_u32(&cl_bar[par]), unsigned(lane)));
+                if (b == 0 && sc.trace && lane == 0) sc.trace[c * 8 + 1] = gtime();
+                mbar_wait(smem_u32(&cl_bar[par]), unsigned(c >> 1) & 1u);
+                if (lane < G) {
+                    gk = ((volatile Msg *)&cl_cand[par][lane])->lo;
+                    gi = int(unsigned(((volatile Msg *)&cl_cand[par][lane])->hi));
+                    gw = lane;
+                }
+            } else
             for (int base = 0; base < G; base += 32) {
                 const int q = min(base + lane, G - 1);
                 unsigned long long lo_;
@@ -416,7 +510,15 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         T *prow_c = prow_s[par];
         // the pivot row arrives (warps 0-1) and, if rows d <-> prow_idx swap inside the panel, goes straight into row d
         // while warps 2-3 bring the old diagonal row into row prow_idx: one phase, one barrier
-        if ((tid & ~31) < jb) {                   // whole warps poll (lanes past jb re-read chunk jb-1)
+        if (CL) {
+            if (tid < jb) {
+                const T v = ld_cluster(&cl_crow[par][tid], unsigned(win));
+                prow_c[tid] = v;
+                if (prow_idx != d && owns_d) s[(d - r0) * PLDS + tid] = v;
+            } else if (prow_idx != d && prow_idx >= r0 && prow_idx < r1 && tid >= 64 && tid < 64 + jb) {
+                s[(prow_idx - r0) * PLDS + (tid - 64)] = ld_cluster(&cl_drow[par][tid - 64], unsigned((d - J) / R));
+            }
+        } else if ((tid & ~31) < jb) {            // whole warps poll (lanes past jb re-read chunk jb-1)
             unsigned long long vlo;
             const Msg *src = sc.rowbuf + size_t(par * GMAX + win) * PW + min(tid, jb - 1);
             while (!chunk_load(src, tag, vlo)) {}
@@ -458,6 +560,7 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         const int r = idx / jb, c = idx - r * jb;
         A[size_t(r0 + r) * ld + J + c] = s[r * PLDS + c];
     }
+    if (CL) cluster_sync_all();                            // remote shared memory stays alive while anyone may still read it
 }
 
 // -------------------------------------------------------------------------------------------
@@ -491,60 +594,6 @@ constexpr int CL_ROWS = CL_WORKERS / 2;                          // rows per CTA
 constexpr int CL_HC = PW / 2;                                    // columns per thread
 constexpr int CL_GC = 16;                                        // columns per pass of the closing gather
 
-__device__ __forceinline__ unsigned smem_u32(const void *p) { return unsigned(__cvta_generic_to_shared(p)); }
-__device__ __forceinline__ unsigned cluster_ctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ unsigned cluster_nctarank() {
-    unsigned r;
-    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ unsigned mapa(unsigned addr, unsigned rank) {
-    unsigned r;
-    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
-    return r;
-}
-__device__ __forceinline__ void mbar_init(unsigned addr, unsigned count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(addr), "r"(count) : "memory");
-}
-// remote 16-byte store that completes 16 tx-bytes on the destination CTA's mbarrier when the data has landed
-__device__ __forceinline__ void st_async_v2(unsigned cluster_addr, unsigned long long lo, unsigned long long hi,
-                                            unsigned cluster_mbar) {
-    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b64 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
-                 "l"(lo), "l"(hi), "r"(cluster_mbar)
-                 : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned addr, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned addr, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(addr), "r"(parity)
-            : "memory");
-    } while (!ok);
-}
-__device__ __forceinline__ double ld_cluster(const double *p, unsigned rank) {
-    unsigned long long v;
-    asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(mapa(smem_u32(p), rank)) : "memory");
-    return __longlong_as_double((long long)v);
-}
-__device__ __forceinline__ float ld_cluster(const float *p, unsigned rank) {
-    unsigned v;
-    asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(mapa(smem_u32(p), rank)) : "memory");
-    return __uint_as_float(v);
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release;\n\tbarrier.cluster.wait.acquire;" ::: "memory");
-}
 __device__ __forceinline__ void worker_sync() { __syncthreads(); }
 
 // One warp folds the interchange (row d <-> row p) into a net permutation over "touched" rows: index i < w is row
@@ -2131,6 +2180,7 @@ int g_lu_gmax_ref();
 int g_lu_dbg_ref();
 int g_lu_cluster_ref();
 int g_lu_slab_rows_ref();
+int g_lu_k3e_rows_ref();
 
 // scratch layout (bytes): packets | rowbuf | diagbuf | result | laswp plan | plan state
 constexpr size_t SC_PACKETS = 0;
@@ -2249,7 +2299,9 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
     // largest cluster each device schedules for the cluster panel kernel (16 needs the non-portable opt-in)
     static int cluster_max_dev[RLA_MAX_DEVICES];
     if (const int od_ = attr_once.pending(); od_ >= 0) {
-        RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        RLA_CUDA(cudaFuncSetAttribute(lu_panel_kernel<T, true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         int cluster_max = 0;
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(size_t(CL_ROWS) * PLDS * sizeof(T))));
         RLA_CUDA(cudaFuncSetAttribute(lu_panel_cluster_kernel<T>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
@@ -2296,8 +2348,30 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
         if (trace_base) sc.trace = trace_base + size_t((j - J0) / PW) * 64 * 8;   // one page per inner panel
         // panels of <= 4096 rows, column-slab kernel: columns dealt to the CTAs, pivot search local to one CTA
         const int slab_rows = g_lu_cluster_ref() == 3 ? SL_MAXROWS : (g_lu_cluster_ref() == 1 ? min(g_lu_slab_rows_ref(), SL_MAXROWS) : 0);
+        // panels whose rows fit the shared memory of ONE cluster (<= 16 x 393 rows in f64): the grid kernel in cluster mode --
+        // rows in shared memory, exchange over DSMEM (lu_cluster 5: wherever it fits; automatic rule: lu_k3e_rows)
+        const int k3e_rows = (cluster_max >= 2) ? min(g_lu_cluster_ref() == 5 ? INT_MAX : (g_lu_cluster_ref() == 1 ? g_lu_k3e_rows_ref() : 0),
+                                                      cluster_max * int((200 * 1024) / (PLDS * sizeof(T)))) : 0;
         if (nrem <= slab_rows) {
             RLA_TRY(launch_slab_panel<T>(ws, a, ld, n, j, jb, ipiv, d_info, sc, J0, w, s));
+        } else if (nrem <= k3e_rows) {
+            const int CS = cluster_max;
+            int R_ = (nrem + CS - 1) / CS, G_ = CS, n__ = n, J_ = j, jb_ = jb, J0_ = J0, w_ = w, dbg_ = g_lu_dbg_ref();
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(2 * CS);                     // cluster 0: the row CTAs; cluster 1: the hub (its other CTAs exit)
+            cfg.blockDim = dim3(PANEL_THREADS);
+            cfg.dynamicSmemBytes = size_t(R_) * PLDS * sizeof(T);
+            cfg.stream = s;
+            cudaLaunchAttribute at[1];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = unsigned(CS);
+            at[0].val.clusterDim.y = 1;
+            at[0].val.clusterDim.z = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            RLA_CUDA(cudaLaunchKernelEx(&cfg, lu_panel_kernel<T, true>, a, ld, n__, J_, jb_, R_, G_, ipiv, d_info, sc, ws.tag, J0_, w_, dbg_));
+            note_launch();
+            ws.tag += unsigned(jb);
         } else
         // panels of <= 16 x 256 rows: one thread-block cluster, panel in registers, exchange over DSMEM
         if (g_lu_cluster_ref() && nrem <= cluster_max * CL_ROWS) {
@@ -2341,7 +2415,7 @@ int factor_block(LuWorkspace &ws, T *a, size_t ld, int n, int J0, int w, int32_t
             int n__ = n, J_ = j, jb_ = jb, R_ = R, G_ = G, J0_ = J0, w_ = w, dbg_ = g_lu_dbg_ref();
             unsigned tag_base = ws.tag;
             void *args[] = {&a_, &ld_, &n__, &J_, &jb_, &R_, &G_, &ipiv, &d_info, &sc, &tag_base, &J0_, &w_, &dbg_};
-            RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T>, dim3(grid), dim3(PANEL_THREADS), args, smem, s));
+            RLA_CUDA(cudaLaunchCooperativeKernel((void *)lu_panel_kernel<T, false>, dim3(grid), dim3(PANEL_THREADS), args, smem, s));
             note_launch();
             ws.tag += unsigned(jb);
         }
@@ -2405,10 +2479,13 @@ int g_lu_dbg = 0;             // rla_set_tuning("lu_dbg", bits): experiments (bi
 int g_lu_cluster = 1;          // rla_set_tuning("lu_cluster", v): panel kernel selection.  0 = always the grid-wide kernel (K3);
                                // 1 (default) = automatic: column-slab kernel (K3d) for panels of <= lu_slab_rows rows, cluster pull
                                // kernel (K3b) up to 4096 rows, K3 above; 2 = pushed-row cluster kernel (K3c, experimental: bit-identical,
-                               // measured slower); 3 = K3d wherever it fits (<= 3840 rows), K3b / K3 above; 4 = K3b / K3 only
+                               // measured slower); 3 = K3d wherever it fits (<= 3840 rows), K3b / K3 above; 4 = K3b / K3 only;
+                               // 5 = K3 in cluster mode (rows in shared memory, DSMEM exchange) wherever one cluster holds the rows
+int g_lu_k3e_rows = 0;         // rla_set_tuning("lu_k3e_rows", v): tallest panel the automatic rule gives to the grid kernel in cluster mode
+                               // (rows in shared memory, exchange over DSMEM); panels of <= lu_slab_rows rows still go to K3d
 int g_lu_slab_rows = 1920;     // rla_set_tuning("lu_slab_rows", v): tallest panel the automatic rule gives to K3d (measured crossover
                                // against K3b: profiles/r02_lu_slab_sweep.jsonl)
-namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } int g_lu_slab_rows_ref() { return g_lu_slab_rows; } }
+namespace { int g_lu_gmax_ref() { return g_lu_gmax; } int g_lu_dbg_ref() { return g_lu_dbg; } int g_lu_cluster_ref() { return g_lu_cluster; } int g_lu_slab_rows_ref() { return g_lu_slab_rows; } int g_lu_k3e_rows_ref() { return g_lu_k3e_rows; } }
 
 int device_num_sms() {
     static std::atomic<int> sms[RLA_MAX_DEVICES];

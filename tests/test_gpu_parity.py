@@ -427,7 +427,7 @@ def test_lu_cluster_panel_identical_to_grid_panel(rla, oracle, dtype):
         cases.append(sing)
         for a in cases:
             g = factor(a, 0)
-            for mode in (1, 2, 3, 4):           # automatic (slab + pull); pushed-row; column-slab wherever it fits; pull only
+            for mode in (1, 2, 3, 4, 5):        # automatic; pushed-row; column-slab wherever it fits; pull only; grid kernel in cluster mode
                 c = factor(a, mode)
                 assert g[2] == c[2], (a.shape, mode)
                 if g[2] == 0:
@@ -475,7 +475,7 @@ def test_lu_panel_kernels_randomized_stress(rla, oracle):
             n = int(rng.choice([130, 256, 300, 511, 640, 1000, 1500, 2048, 2500, 3333, 4096]))
             a0 = torch.from_numpy(oracle.fill_uniform((n, n), 9000 + trial, np.float64, lo=-0.5, scale=1.0)).cuda()
             g = factor(a0, 0)
-            for mode in (1, 2, 3, 4):
+            for mode in (1, 2, 3, 4, 5):
                 c = factor(a0, mode)
                 torch.cuda.synchronize()
                 assert int(g[2].item()) == int(c[2].item()) == 0

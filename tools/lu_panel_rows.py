@@ -7,11 +7,11 @@ import rulinalg_b200 as rla
 l = rla.lib(); rla.check(l.rla_init(0))
 s = torch.cuda.current_stream().cuda_stream
 plan = torch.empty(int(l.rla_lu_plan_bytes()), dtype=torch.uint8, device="cuda")
-for n in (64, 128, 256, 480, 700, 960, 1400, 1920, 2800, 3840, 4096):
+for n in (64, 128, 256, 480, 700, 960, 1400, 1920, 2800, 3840, 4096, 5000, 6200):
     torch.manual_seed(n)
     a0 = torch.rand(n, 64, dtype=torch.float64, device="cuda") - 0.5
     out = dict(rows=n)
-    for mode, name in ((0, "grid_K3"), (4, "cluster_K3b"), (3, "slab_K3d")):
+    for mode, name in ((0, "grid_K3"), (5, "grid_cluster_K3e"), (4, "cluster_K3b"), (3, "slab_K3d")):
         l.rla_set_tuning(b"lu_cluster", mode)
         best = 1e30
         for rep in range(6):
