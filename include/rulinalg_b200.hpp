@@ -157,6 +157,22 @@ template <typename T> Matrix<T> operator*(const MatrixSlice<T> &a, const Matrix<
 template <typename T> Matrix<T> operator*(const Matrix<T> &a, const MatrixSlice<T> &b) { return mat_mul_general<T>(a, b); }
 template <typename T> Matrix<T> operator*(const MatrixSlice<T> &a, const MatrixSlice<T> &b) { return mat_mul_general<T>(a, b); }
 
+// Held operands (rla_operand_hold / rla_operand_release): while the guard lives the matrix is promised immutable -- it is
+// only reachable through `const Matrix<T> &` here -- so products, solves and matrix-vector calls that read it find its copy
+// resident in HBM instead of uploading it again (the repeated products of lu.rs:789,907, eigen.rs:114-148).
+template <typename T>
+class Held {
+  public:
+    explicit Held(const Matrix<T> &m) : p_(m.rows() * m.cols() ? m.as_ptr() : nullptr) {
+        if (p_) detail::check(rla_operand_hold(p_, m.rows() * m.cols() * sizeof(T)));
+    }
+    ~Held() { if (p_) rla_operand_release(p_); }
+    Held(const Held &) = delete;
+    Held &operator=(const Held &) = delete;
+  private:
+    const void *p_;
+};
+
 class PermutationMatrix {
   public:
     PermutationMatrix() = default;
@@ -203,8 +219,21 @@ class PartialPivLu {
         PartialPivLu out;
         out.lu_ = std::move(matrix);
         out.p_ = PermutationMatrix(std::move(perm));
+        out.hold_();         // the factors never change again: every solve() after the first finds them resident in HBM
         return out;
     }
+    PartialPivLu() = default;
+    PartialPivLu(const PartialPivLu &o) : lu_(o.lu_), p_(o.p_) { hold_(); }
+    PartialPivLu(PartialPivLu &&o) noexcept : lu_(std::move(o.lu_)), p_(std::move(o.p_)), held_(o.held_) { o.held_ = false; }
+    PartialPivLu &operator=(PartialPivLu o) {
+        release_();
+        lu_ = std::move(o.lu_);          // the vector's heap block (the held range) moves with it
+        p_ = std::move(o.p_);
+        held_ = o.held_;
+        o.held_ = false;
+        return *this;
+    }
+    ~PartialPivLu() { release_(); }
     // lu.rs:231-244
     Vector<T> solve(Vector<T> b) const {
         if (b.size() != lu_.rows()) throw Panic("Right-hand side vector must have compatible size.");
@@ -221,8 +250,17 @@ class PartialPivLu {
     const Matrix<T> &lu() const { return lu_; }
     const PermutationMatrix &p() const { return p_; }
   private:
+    void hold_() {
+        const size_t bytes = lu_.rows() * lu_.cols() * sizeof(T);
+        held_ = bytes != 0 && rla_operand_hold(lu_.as_ptr(), bytes) == RLA_OK;
+    }
+    void release_() {
+        if (held_) rla_operand_release(lu_.as_ptr());
+        held_ = false;
+    }
     Matrix<T> lu_;
     PermutationMatrix p_;
+    bool held_ = false;
 };
 
 // Cholesky<T> (src/matrix/decomposition/cholesky.rs:94-245)
