@@ -145,3 +145,27 @@ def test_multi_device_entry_points_fail_loudly_without_gpu(rla):
     assert l.rla_set_devices(2) == rla._lib.RLA_ERR_NO_DEVICE if hasattr(rla, "_lib") else l.rla_set_devices(2) == -3
     assert l.rla_get_devices() == 1
     assert l.rla_shutdown() == 0
+
+
+def test_operand_hold_bookkeeping_needs_no_device(rla):
+    # rla_operand_hold / rla_operand_release are host-side declarations: nesting, mismatched ranges and
+    # unknown pointers are answered without touching a GPU; nothing is resident until a product actually runs
+    lib = rla.lib()
+    a = np.zeros((64, 64))
+    p, nb = a.ctypes.data, a.nbytes
+    assert lib.rla_operand_resident_bytes() == 0
+    assert lib.rla_operand_hold(0, nb) != 0 and lib.rla_operand_hold(p, 0) != 0
+    assert lib.rla_operand_hold(p, nb) == 0
+    assert lib.rla_operand_hold(p, nb) == 0            # nests
+    assert lib.rla_operand_hold(p, nb - 8) != 0        # same base, different range
+    assert lib.rla_operand_release(p + 8) != 0         # not a held base
+    assert lib.rla_operand_release(p) == 0
+    assert lib.rla_operand_release(p) == 0
+    assert lib.rla_operand_release(p) != 0             # nothing left
+    assert lib.rla_operand_resident_bytes() == 0
+    m = rla.Matrix.from_numpy(a, copy=False)
+    with m.held() as same:
+        assert same is m and not a.flags.writeable     # numpy's stand-in for the shared borrow
+        with pytest.raises(ValueError):
+            a[0, 0] = 1.0
+    assert a.flags.writeable
