@@ -552,9 +552,11 @@ lu_panel_kernel(T *__restrict__ A, size_t ld, int n, int J, int jb, int R, int G
         } else {
             for (int r = lo2 + tid; r < nrows; r += PANEL_THREADS) s[r * PLDS + c] = div_rn(s[r * PLDS + c], piv);
         }
-        __syncthreads();
+        // no CTA barrier here: the next column's scan reads, per thread, exactly the rows this thread has just written
+        // (same r = lo + tid mapping); everything that crosses threads is behind the barrier after the warp candidates
         if (b == 0) TRACE(4);
     }
+    __syncthreads();
 
     for (int idx = tid; idx < nrows * jb; idx += PANEL_THREADS) {
         const int r = idx / jb, c = idx - r * jb;
