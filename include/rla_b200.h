@@ -253,13 +253,23 @@ RLA_API int rla_fill_uniform_f64_dev(double *dst, size_t rows, size_t cols, size
 RLA_API int rla_fill_uniform_f32_dev(float *dst, size_t rows, size_t cols, size_t ld, uint64_t seed,
                              uint64_t offset, float lo, float scale, void *stream);
 
-/* Tuning knobs (development / benchmarking).  "dgemm_cfg": -1 = auto (default), 0..7 = a fixed CTA shape
- * (see csrc/dgemm.cu).  "lu_gmax": cap on the panel kernel's row
- * CTAs.  "lu_cluster": 1 (default) = panels that fit one thread-block cluster use the DSMEM panel kernel, 0 = always
- * the grid-wide kernel.  "host_gemm_2d": 1 (default) = 2-D wavefront pipeline for large host-pointer products, 0 = row panels;
- * "host_gemm_s": strips per dimension of that pipeline, 0 (default) = auto.  "host_gemm_grade": 1 = graded (smaller) first and last strips in that pipeline (default 0: no measurable gain).  "host_stage": 1 (default) = pageable host
- * operands of large calls travel through the library's pinned staging ring (host.cu), 0 = plain cudaMemcpyAsync on them.
- * "lu_dbg": timing experiments only.  Returns RLA_ERR_INVALID for unknown keys. */
+/* Tuning knobs (development / benchmarking); defaults are the measured best.  Unknown keys: RLA_ERR_INVALID.
+ *   "dgemm_cfg"        -1 = auto (default), 0..7 = a fixed CTA shape (csrc/dgemm.cu); "sgemm_cfg": -1 auto, 0 = 128x128, 1 = 64x128
+ *   "dgemm_streamk"    0 (default) = tiled kernels only; 2 / 3 = the 128x128 / 64x64 stream-K variant whenever operands are aligned
+ *   "lu_cluster"       LU panel kernel: 1 (default) = automatic (column-slab kernel up to "lu_slab_rows" rows, cluster kernel up
+ *                      to 4096, grid kernel above); 0 = grid kernel only; 2 = pushed-row cluster kernel; 3 = column-slab kernel
+ *                      wherever it fits; 4 = cluster + grid kernels only; 5 = grid kernel in cluster mode wherever it fits
+ *   "lu_slab_rows"     tallest panel the automatic rule gives to the column-slab kernel (default 1920)
+ *   "lu_k3e_rows"      tallest panel the automatic rule gives to the grid kernel's cluster mode (default 0 = never)
+ *   "lu_gmax"          cap on the grid panel kernel's row CTAs (default 32)
+ *   "host_gemm_2d"     1 (default) = 2-D wavefront pipeline for large host-pointer products, 0 = row panels
+ *   "host_gemm_s"      strips per dimension of that pipeline, 0 (default) = auto
+ *   "host_gemm_kprefix" sixteenths of the k range uploaded and multiplied as rank-kc updates before the wavefront starts;
+ *                      -1 (default) = k/4 when k >= 4096, 0 = off;  "host_gemm_kchunk": kc (default 256)
+ *   "host_gemm_grade"  1 = graded first / last strips in that pipeline (default 0: no measurable gain)
+ *   "host_stage"       1 (default) = pageable host operands of large calls travel through the library's pinned staging ring
+ *                      (host.cu), 0 = plain cudaMemcpyAsync on them
+ *   "lu_dbg"           timing experiments only */
 RLA_API int rla_set_tuning(const char *key, int value);
 
 /* Roofline denominators measured on the current device: issue-bound register loops on every SM.
