@@ -400,6 +400,13 @@ class PartialPivLu:
         """Return the device-resident copy of the factors (solve() then re-uploads `lu` / `p`)."""
         self.__del__()
 
+    def held(self):
+        """`with lu.held(): ...` -- the factors are promised immutable inside the block (rla_operand_hold), so solve() and
+        inverse() find them resident in HBM after the first call: f32 as well, and without the f64 handle.  The Rust and C++
+        mirrors hold for the whole lifetime of the struct (its `lu` is private there); here the fields are public, so it is
+        explicit."""
+        return self.lu.held()
+
     def __enter__(self):
         return self
 
