@@ -169,3 +169,13 @@ def test_operand_hold_bookkeeping_needs_no_device(rla):
         with pytest.raises(ValueError):
             a[0, 0] = 1.0
     assert a.flags.writeable
+
+
+def test_every_tuning_key_is_documented_in_the_header():
+    # rla_set_tuning keys are part of what a maintainer sees: api.cu and the header comment must list the same set
+    src = open(os.path.join(ROOT, "rulinalg_b200", "csrc", "api.cu")).read()
+    keys = set(re.findall(r'strcmp\(key, "(\w+)"\)', src))
+    hdr = open(os.path.join(ROOT, "include", "rla_b200.h")).read()
+    doc = hdr[hdr.index("Tuning knobs"):hdr.index("RLA_API int rla_set_tuning")]
+    documented = set(re.findall(r'"(\w+)"', doc))
+    assert keys and keys == documented, (sorted(keys - documented), sorted(documented - keys))
